@@ -1,0 +1,190 @@
+// feo_common.cuh -- shared host/device plumbing of libfeotensor_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <limits>
+#include <string>
+#include <type_traits>
+
+#include "../../include/feotensor_b200.h"
+
+// ---- context ------------------------------------------------------------------------------------
+enum feo_knob {
+    FEO_KNOB_BCAST_TILE = 0,    // 0 = auto, 1 = 8x4, 2 = 4x4, 3 = 1x1 (generic vector), 4 = scalar fallback
+    FEO_KNOB_REDUCE_SPLIT = 1,  // 0 = auto, else forced number of splits S
+    FEO_KNOB_REDUCE_BLOCKS_PER_SM = 2,  // target resident blocks per SM used by the split planner (0 = auto)
+    FEO_KNOB_MATMUL_TF32_STAGES = 3,
+    FEO_KNOB_COUNT = 8
+};
+
+struct feo_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;      // stream in use
+    cudaStream_t own_stream = nullptr;  // stream created by feo_init
+    void *workspace = nullptr;          // scratch for two-stage reductions
+    size_t workspace_bytes = 0;
+    int *arith_flag = nullptr;          // device int, sticky
+    uint64_t launches = 0;
+    int knobs[FEO_KNOB_COUNT] = {0};
+    std::string last_error;
+};
+
+int feo_fail(feo_ctx *ctx, int status, const char *fmt, ...);
+int feo_workspace(feo_ctx *ctx, size_t bytes, void **ptr);
+
+#define FEO_CUDA(ctx, expr)                                                                       \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return feo_fail((ctx), FEO_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                            __FILE__, __LINE__);                                                  \
+    } while (0)
+
+#define FEO_LAUNCH_CHECK(ctx)          \
+    do {                               \
+        (ctx)->launches++;             \
+        FEO_CUDA(ctx, cudaGetLastError()); \
+    } while (0)
+
+// dtype dispatch: FEO_DISPATCH(dtype, T, { ... code using T ... })
+#define FEO_DISPATCH(ctx, dtype, T, ...)                                         \
+    switch (dtype) {                                                             \
+    case FEO_F32: { using T = float; __VA_ARGS__; break; }                       \
+    case FEO_F64: { using T = double; __VA_ARGS__; break; }                      \
+    case FEO_I32: { using T = int32_t; __VA_ARGS__; break; }                     \
+    case FEO_I64: { using T = int64_t; __VA_ARGS__; break; }                     \
+    case FEO_U32: { using T = uint32_t; __VA_ARGS__; break; }                    \
+    default: return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "unsupported dtype %d", (int)(dtype)); \
+    }
+
+// ---- element arithmetic -------------------------------------------------------------------------
+// Integers wrap like Rust release builds (arithmetic done in the unsigned twin); floats are one
+// IEEE operation per call (the library is built without fast-math; nothing here can contract).
+template <typename T> struct UnsignedOf { using type = T; };
+template <> struct UnsignedOf<int32_t> { using type = uint32_t; };
+template <> struct UnsignedOf<int64_t> { using type = unsigned long long; };
+
+template <typename T> __host__ __device__ __forceinline__ T w_add(T a, T b) {
+    if constexpr (std::is_floating_point<T>::value) return a + b;
+    else { using U = typename UnsignedOf<T>::type; return (T)((U)a + (U)b); }
+}
+template <typename T> __host__ __device__ __forceinline__ T w_sub(T a, T b) {
+    if constexpr (std::is_floating_point<T>::value) return a - b;
+    else { using U = typename UnsignedOf<T>::type; return (T)((U)a - (U)b); }
+}
+template <typename T> __host__ __device__ __forceinline__ T w_mul(T a, T b) {
+    if constexpr (std::is_floating_point<T>::value) return a * b;
+    else { using U = typename UnsignedOf<T>::type; return (T)((U)a * (U)b); }
+}
+// Division: floats IEEE; integers write 0 and raise the sticky flag on x/0 and MIN/-1 (Rust panics).
+template <typename T> __device__ __forceinline__ T w_div(T a, T b, int *flag) {
+    if constexpr (std::is_floating_point<T>::value) {
+        return a / b;
+    } else {
+        bool bad = (b == (T)0);
+        if constexpr (std::is_signed<T>::value) bad = bad || (a == std::numeric_limits<T>::min() && b == (T)-1);
+        if (bad) { if (flag) atomicOr(flag, 1); return (T)0; }
+        return a / b;
+    }
+}
+template <int OP, typename T> __device__ __forceinline__ T apply_op(T a, T b, int *flag) {
+    if constexpr (OP == FEO_ADD) return w_add(a, b);
+    else if constexpr (OP == FEO_SUB) return w_sub(a, b);
+    else if constexpr (OP == FEO_MUL) return w_mul(a, b);
+    else return w_div(a, b, flag);
+}
+
+// ---- 128-bit (and narrower) vector access ---------------------------------------------------------
+template <typename T, int N> struct alignas(sizeof(T) * N) AVec { T v[N]; };
+template <typename T> struct VecN { static constexpr int value = 16 / sizeof(T); };
+
+// Streaming (read-once) load: bypass L1 allocation.
+template <typename V> __device__ __forceinline__ V ld_stream(const V *p) {
+    static_assert(sizeof(V) == 16 || sizeof(V) == 8 || sizeof(V) == 4, "vector size");
+    V r;
+    if constexpr (sizeof(V) == 16) {
+        uint4 t;
+        asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
+        __builtin_memcpy(&r, &t, 16);
+    } else if constexpr (sizeof(V) == 8) {
+        uint2 t;
+        asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(t.x), "=r"(t.y) : "l"(p));
+        __builtin_memcpy(&r, &t, 8);
+    } else {
+        uint32_t t;
+        asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(t) : "l"(p));
+        __builtin_memcpy(&r, &t, 4);
+    }
+    return r;
+}
+// Reused (keep in L1/L2) read-only load.
+template <typename V> __device__ __forceinline__ V ld_keep(const V *p) {
+    V r;
+    if constexpr (sizeof(V) == 16) {
+        uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
+        __builtin_memcpy(&r, &t, 16);
+    } else if constexpr (sizeof(V) == 8) {
+        uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+        __builtin_memcpy(&r, &t, 8);
+    } else {
+        uint32_t t = __ldg(reinterpret_cast<const uint32_t *>(p));
+        __builtin_memcpy(&r, &t, 4);
+    }
+    return r;
+}
+// Streaming store (evict-first): results are written once and not re-read by the kernel.
+template <typename V> __device__ __forceinline__ void st_stream(V *p, const V &v) {
+    if constexpr (sizeof(V) == 16) {
+        uint4 t; __builtin_memcpy(&t, &v, 16);
+        asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w) : "memory");
+    } else if constexpr (sizeof(V) == 8) {
+        uint2 t; __builtin_memcpy(&t, &v, 8);
+        asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(t.x), "r"(t.y) : "memory");
+    } else {
+        uint32_t t; __builtin_memcpy(&t, &v, 4);
+        asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(t) : "memory");
+    }
+}
+
+static inline bool feo_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline size_t feo_ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+
+// ---- entry points implemented per kernel family (called from feo_api.cu) ---------------------------
+int feo_impl_ewise(feo_ctx *ctx, int op, int dtype, void *out, const void *a, const void *b, const void *scalar_host, size_t n);
+int feo_impl_broadcast(feo_ctx *ctx, int op, int dtype, void *out, const void *a, const void *b, int rank,
+                       const size_t *shape, const size_t *sa, const size_t *sb);
+int feo_impl_fill(feo_ctx *ctx, int dtype, void *out, const void *value, size_t n);
+int feo_impl_eye(feo_ctx *ctx, int dtype, void *out, size_t rows, size_t cols);
+int feo_impl_fill_uniform(feo_ctx *ctx, int dtype, void *out, size_t n, uint64_t seed, uint64_t first_index, double lo, double hi);
+
+// reduce `mode`: 0 final result, 1 partial (no division; VAR writes mean|M2), 2 squared deviations from aux
+int feo_impl_reduce(feo_ctx *ctx, int kind, int dtype, void *out, const void *in, const void *aux, int rank,
+                    const size_t *shape, int naxes, const size_t *axes, int mode);
+int feo_impl_var_merge(feo_ctx *ctx, int dtype, void *out, const void *partials, size_t nparts, size_t nout,
+                       size_t count_per_part, const void *divisor_host);
+// loader: 1 = a[i]*b[i] rows (dot / batched dot), 2 = A[i,j]*v[j] (matvec), 3 = v[i]*A[i,j] (vecmat)
+int feo_impl_dotlike(feo_ctx *ctx, int loader, int dtype, void *out, const void *a, const void *b, size_t outer, size_t inner);
+int feo_impl_matmul_simt(feo_ctx *ctx, int dtype, void *C, const void *A, const void *B, size_t M, size_t K, size_t N);
+int feo_impl_matmul_tf32x3(feo_ctx *ctx, void *C, const void *A, const void *B, size_t M, size_t K, size_t N);
+bool feo_matmul_tf32x3_supported(size_t M, size_t K, size_t N);
+
+// Closed form of the reference's count-in-T (tensor.rs:112-121): floats saturate, integers wrap.
+template <typename T> static inline T feo_count_in_type(size_t count) {
+    if constexpr (std::is_same<T, float>::value) return (float)(count < (size_t(1) << 24) ? count : (size_t(1) << 24));
+    else if constexpr (std::is_same<T, double>::value) return (double)(count < (size_t(1) << 53) ? count : (size_t(1) << 53));
+    else return (T)count;  // modular conversion == repeated wrapping +1
+}
+template <typename T> static inline T feo_divisor(int rank, const size_t *shape, int naxes, const size_t *axes) {
+    if (naxes > 0) {
+        T n = (T)1;
+        for (int i = 0; i < naxes; ++i) n = w_mul(n, feo_count_in_type<T>(shape[axes[i]]));
+        return n;
+    }
+    size_t size = 1;
+    for (int d = 0; d < rank; ++d) size *= shape[d];
+    return feo_count_in_type<T>(size);
+}

@@ -1,0 +1,560 @@
+// reduce_kernels.cuh -- K2/K3/K5: axis reductions (tensor.rs:70-307), dot (vector.rs:71-78),
+// matrix.vector (matrix.rs:92-103) and vector.matrix (vector.rs:80-91) for sm_100a.
+//
+// Geometry.  A dense row-major tensor with some axes reduced collapses (extent-1 dims dropped,
+// neighbours with the same kept/reduced status merged) to alternating groups.  Up to four groups
+// fit the canonical form  in[k1][r1][k2][r2] -> out[k1][k2]  (any extent may be 1):
+//   cols  kernel  r2 == 1        kept axis innermost: threads along k2 (128-bit), loop over r1
+//   micro kernel  2 <= r2 <= 32  short reduced innermost axis: one thread per output, r2 contiguous
+//                                elements (128-bit loads) per r1 step
+//   rows  kernel  r2 > 32        long reduced innermost axis: a warp or a block per output, lanes
+//                                stride the row with 128-bit loads, warp-shuffle + shared-memory tree
+//   generic       anything else  (more than four groups): a block per output, div/mod indexing
+// Too few outputs to fill 148 SMs -> the reduced range is split S ways, stage 1 writes accumulators
+// to a workspace and a deterministic stage 2 merges them in split order (no atomics anywhere).
+// One pass over the input for every kind: HBM-bound, algorithmic bytes = sizeof(T)*(N_in + N_out).
+#pragma once
+
+#include "feo_common.cuh"
+
+namespace feo_red {
+
+constexpr int kThreads = 256;
+enum { K_SUM = 0, K_MAX = 1, K_MIN = 2, K_WELFORD = 3, K_SQDEV = 4 };
+enum { FIN_NONE = 0, FIN_DIV = 1, FIN_VAR = 2, FIN_MEAN_M2 = 3 };
+enum { LD_PLAIN = 0, LD_MUL = 1, LD_MATVEC = 2, LD_VECMAT = 3 };
+
+// ---- accumulators ---------------------------------------------------------------------------------
+template <typename T, int KIND> struct Acc;
+
+template <typename T> struct Acc<T, K_SUM> {
+    T v;
+    __device__ __forceinline__ void init(T) { v = (T)0; }
+    __device__ __forceinline__ void push(T x) { v = w_add(v, x); }
+    __device__ __forceinline__ void merge(const Acc &o) { v = w_add(v, o.v); }
+    template <int N> __device__ __forceinline__ void push_batch(const T (&x)[N]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) push(x[i]);
+    }
+};
+template <typename T> struct Acc<T, K_SQDEV> {  // sum of (x - mean)^2 for a given mean (integer var, tensor.rs:196-198)
+    T v, m;
+    __device__ __forceinline__ void init(T mean) { v = (T)0; m = mean; }
+    __device__ __forceinline__ void push(T x) { const T c = w_sub(x, m); v = w_add(v, w_mul(c, c)); }
+    __device__ __forceinline__ void merge(const Acc &o) { v = w_add(v, o.v); }
+    template <int N> __device__ __forceinline__ void push_batch(const T (&x)[N]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) push(x[i]);
+    }
+};
+template <typename T> struct Acc<T, K_MAX> {
+    T v;
+    __device__ __forceinline__ void init(T) { v = std::numeric_limits<T>::lowest(); }
+    __device__ __forceinline__ void push(T x) { v = (x > v) ? x : v; }  // strict compare, tensor.rs:248
+    __device__ __forceinline__ void merge(const Acc &o) { push(o.v); }
+    template <int N> __device__ __forceinline__ void push_batch(const T (&x)[N]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) push(x[i]);
+    }
+};
+template <typename T> struct Acc<T, K_MIN> {
+    T v;
+    __device__ __forceinline__ void init(T) { v = std::numeric_limits<T>::max(); }
+    __device__ __forceinline__ void push(T x) { v = (x < v) ? x : v; }  // tensor.rs:300
+    __device__ __forceinline__ void merge(const Acc &o) { push(o.v); }
+    template <int N> __device__ __forceinline__ void push_batch(const T (&x)[N]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) push(x[i]);
+    }
+};
+// Welford / Chan: (count, mean, M2).  Batches are combined two-pass in registers and merged with one
+// division per batch, so the per-element cost stays ~4 flops while keeping Welford's stability.
+template <typename T> struct Acc<T, K_WELFORD> {
+    T n, mean, m2;
+    __device__ __forceinline__ void init(T) { n = (T)0; mean = (T)0; m2 = (T)0; }
+    __device__ __forceinline__ void push(T x) {
+        n += (T)1;
+        const T d = x - mean;
+        mean += d / n;
+        m2 += d * (x - mean);
+    }
+    __device__ __forceinline__ void merge_raw(T on, T omean, T om2) {
+        if (on == (T)0) return;
+        const T nn = n + on;
+        const T d = omean - mean;
+        const T f = on / nn;
+        mean += d * f;
+        m2 += om2 + d * d * n * f;
+        n = nn;
+    }
+    __device__ __forceinline__ void merge(const Acc &o) { merge_raw(o.n, o.mean, o.m2); }
+    template <int N> __device__ __forceinline__ void push_batch(const T (&x)[N]) {
+        T s = (T)0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) s += x[i];
+        const T bm = s * ((T)1 / (T)N);
+        T q = (T)0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { const T c = x[i] - bm; q += c * c; }
+        merge_raw((T)N, bm, q);
+    }
+};
+
+template <int KIND, typename T> __device__ __forceinline__ T aux_val(const T *aux, long long o) {
+    if constexpr (KIND == K_SQDEV) return aux[o];
+    else return (T)0;
+}
+
+template <typename T> __device__ __forceinline__ T shfl_down_t(T v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
+template <> __device__ __forceinline__ int64_t shfl_down_t<int64_t>(int64_t v, int off) {
+    return (int64_t)__shfl_down_sync(0xffffffffu, (long long)v, off);
+}
+template <typename T, int KIND> __device__ __forceinline__ Acc<T, KIND> shfl_down_acc(const Acc<T, KIND> &a, int off) {
+    Acc<T, KIND> r;
+    if constexpr (KIND == K_WELFORD) {
+        r.n = shfl_down_t(a.n, off); r.mean = shfl_down_t(a.mean, off); r.m2 = shfl_down_t(a.m2, off);
+    } else if constexpr (KIND == K_SQDEV) {
+        r.v = shfl_down_t(a.v, off); r.m = a.m;
+    } else {
+        r.v = shfl_down_t(a.v, off);
+    }
+    return r;
+}
+template <typename T, int KIND> __device__ __forceinline__ void warp_merge(Acc<T, KIND> &a) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { const Acc<T, KIND> o = shfl_down_acc(a, off); a.merge(o); }
+}
+
+template <typename T, int KIND>
+__device__ __forceinline__ void finalize(const Acc<T, KIND> &acc, T *out, long long o, long long nout, int fin, T divisor, int *flag) {
+    if constexpr (KIND == K_WELFORD) {
+        if (fin == FIN_MEAN_M2) { out[o] = acc.mean; out[nout + o] = acc.m2; }
+        else out[o] = acc.m2 / divisor;
+    } else {
+        T v = acc.v;
+        if (fin == FIN_DIV) v = w_div(v, divisor, flag);
+        out[o] = v;
+    }
+}
+template <typename T, int KIND>
+__device__ __forceinline__ void emit(const Acc<T, KIND> &acc, T *out, void *partial, long long o, long long s, long long nout,
+                                     long long S, int fin, T divisor, int *flag) {
+    if (S > 1) reinterpret_cast<Acc<T, KIND> *>(partial)[s * nout + o] = acc;
+    else finalize(acc, out, o, nout, fin, divisor, flag);
+}
+
+struct Geom {
+    long long K1, R1, K2, R2;  // canonical extents
+    long long S, S1, S2;       // splits: S = S1 (over r1) * S2 (over r2 vectors)
+    long long c1, c2;          // chunk sizes: r1 rows per split, r2 vectors per split
+    long long nout;            // K1 * K2
+    long long xblocks;         // blocks along the thread-mapped axis
+    int fin;
+    int lanes;                 // rows kernel: 32 (warp per output) or 256 (block per output)
+};
+
+// ---- cols: in[k1][r1][k2] -> out[k1][k2], threads along k2 ---------------------------------------------
+template <typename T, int KIND, int LOADER, bool VEC>
+__global__ void __launch_bounds__(kThreads) reduce_cols_kernel(T *__restrict__ out, void *__restrict__ partial,
+                                                               const T *__restrict__ in, const T *__restrict__ in2,
+                                                               const T *__restrict__ aux, const __grid_constant__ Geom G,
+                                                               T divisor, int *flag) {
+    constexpr int W = VEC ? VecN<T>::value : 1;
+    constexpr int U = 8;
+    using V = AVec<T, W>;
+    long long blk = blockIdx.x;
+    const long long bx = blk % G.xblocks; blk /= G.xblocks;
+    const long long s = blk % G.S;
+    const long long k1 = blk / G.S;
+    const long long kv = bx * kThreads + threadIdx.x;
+    if (kv * W >= G.K2) return;
+    const long long r_lo = s * G.c1;
+    const long long r_hi = (r_lo + G.c1 < G.R1) ? r_lo + G.c1 : G.R1;
+    const long long o0 = k1 * G.K2 + kv * W;
+    const T *base = in + (k1 * G.R1) * G.K2 + kv * W;
+    Acc<T, KIND> acc[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) acc[k].init(aux_val<KIND>(aux, o0 + k));
+    long long r = r_lo;
+    for (; r + U <= r_hi; r += U) {
+        V v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = ld_stream(reinterpret_cast<const V *>(base + (r + u) * G.K2));
+        if constexpr (LOADER == LD_VECMAT) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const T w = __ldg(in2 + r + u);
+#pragma unroll
+                for (int k = 0; k < W; ++k) v[u].v[k] = w_mul(w, v[u].v[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            T x[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) x[u] = v[u].v[k];
+            acc[k].push_batch(x);
+        }
+    }
+    for (; r < r_hi; ++r) {
+        V v = ld_stream(reinterpret_cast<const V *>(base + r * G.K2));
+        if constexpr (LOADER == LD_VECMAT) {
+            const T w = __ldg(in2 + r);
+#pragma unroll
+            for (int k = 0; k < W; ++k) v.v[k] = w_mul(w, v.v[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < W; ++k) acc[k].push(v.v[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < W; ++k) emit(acc[k], out, partial, o0 + k, s, G.nout, G.S, G.fin, divisor, flag);
+}
+
+// ---- micro: in[k1][r1][k2][r2] with 2 <= r2 <= 32, one thread per output ---------------------------------
+// R2C > 0: compile-time r2 (vector loads); R2C == 0: run-time r2, scalar loads.
+template <typename T, int KIND, int R2C>
+__global__ void __launch_bounds__(kThreads) reduce_micro_kernel(T *__restrict__ out, void *__restrict__ partial,
+                                                                const T *__restrict__ in, const T *__restrict__ aux,
+                                                                const __grid_constant__ Geom G, T divisor, int *flag) {
+    long long blk = blockIdx.x;
+    const long long bx = blk % G.xblocks; blk /= G.xblocks;
+    const long long s = blk % G.S;
+    const long long k1 = blk / G.S;
+    const long long k2 = bx * kThreads + threadIdx.x;
+    if (k2 >= G.K2) return;
+    const long long r_lo = s * G.c1;
+    const long long r_hi = (r_lo + G.c1 < G.R1) ? r_lo + G.c1 : G.R1;
+    const long long o = k1 * G.K2 + k2;
+    const long long rstride = G.K2 * G.R2;
+    const T *base = in + ((k1 * G.R1) * G.K2 + k2) * G.R2;
+    Acc<T, KIND> acc;
+    acc.init(aux_val<KIND>(aux, o));
+    if constexpr (R2C > 0) {
+        constexpr int VN = VecN<T>::value;
+        constexpr int W = R2C < VN ? R2C : VN;
+        constexpr int NV = R2C / W;
+        constexpr int U = (32 / R2C) > 0 ? ((32 / R2C) > 8 ? 8 : (32 / R2C)) : 1;
+        using V = AVec<T, W>;
+        long long r = r_lo;
+        for (; r + U <= r_hi; r += U) {
+            V v[U][NV];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int j = 0; j < NV; ++j) v[u][j] = ld_stream(reinterpret_cast<const V *>(base + (r + u) * rstride) + j);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                T x[R2C];
+#pragma unroll
+                for (int j = 0; j < NV; ++j)
+#pragma unroll
+                    for (int k = 0; k < W; ++k) x[j * W + k] = v[u][j].v[k];
+                acc.push_batch(x);
+            }
+        }
+        for (; r < r_hi; ++r) {
+            T x[R2C];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const V v = ld_stream(reinterpret_cast<const V *>(base + r * rstride) + j);
+#pragma unroll
+                for (int k = 0; k < W; ++k) x[j * W + k] = v.v[k];
+            }
+            acc.push_batch(x);
+        }
+    } else {
+        for (long long r = r_lo; r < r_hi; ++r) {
+            const T *p = base + r * rstride;
+            for (long long j = 0; j < G.R2; ++j) acc.push(__ldg(p + j));
+        }
+    }
+    emit(acc, out, partial, o, s, G.nout, G.S, G.fin, divisor, flag);
+}
+
+// ---- rows: in[k1][r1][k2][r2], long r2; `lanes` threads cooperate on one output ----------------------------
+template <typename T, int KIND, int LOADER, bool VEC>
+__global__ void __launch_bounds__(kThreads) reduce_rows_kernel(T *__restrict__ out, void *__restrict__ partial,
+                                                               const T *__restrict__ in, const T *__restrict__ in2,
+                                                               const T *__restrict__ aux, const __grid_constant__ Geom G,
+                                                               T divisor, int *flag) {
+    constexpr int W = VEC ? VecN<T>::value : 1;
+    constexpr int U = 4;
+    using V = AVec<T, W>;
+    __shared__ Acc<T, KIND> smem[kThreads / 32];
+    const int lanes = G.lanes;
+    const int per_block = kThreads / lanes;  // outputs (x splits) handled by one block
+    const int sub = threadIdx.x / lanes;     // which of them this thread works on
+    const int lane = threadIdx.x % lanes;
+    const long long unit = (long long)blockIdx.x * per_block + sub;  // = o * S + s
+    const bool active = unit < G.nout * G.S;
+    Acc<T, KIND> acc;
+    long long o = 0, s = 0;
+    if (active) {
+        o = unit / G.S; s = unit % G.S;
+        const long long k1 = o / G.K2, k2 = o % G.K2;
+        const long long s1 = s / G.S2, s2 = s % G.S2;
+        const long long r_lo = s1 * G.c1, r_hi = (r_lo + G.c1 < G.R1) ? r_lo + G.c1 : G.R1;
+        const long long nvec = G.R2 / W;
+        const long long c_lo = s2 * G.c2, c_hi = (c_lo + G.c2 < nvec) ? c_lo + G.c2 : nvec;
+        const long long rstride = G.K2 * G.R2;
+        const long long obase = ((k1 * G.R1) * G.K2 + k2) * G.R2;
+        acc.init(aux_val<KIND>(aux, o));
+        for (long long r = r_lo; r < r_hi; ++r) {
+            const T *row = in + obase + r * rstride;
+            const T *row2 = nullptr;
+            if constexpr (LOADER == LD_MUL) row2 = in2 + obase + r * rstride;
+            if constexpr (LOADER == LD_MATVEC) row2 = in2;
+            long long cv = c_lo + lane;
+            for (; cv + (long long)(U - 1) * lanes < c_hi; cv += (long long)U * lanes) {
+                V v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) v[u] = ld_stream(reinterpret_cast<const V *>(row) + cv + (long long)u * lanes);
+                if constexpr (LOADER == LD_MUL || LOADER == LD_MATVEC) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const V w = (LOADER == LD_MUL) ? ld_stream(reinterpret_cast<const V *>(row2) + cv + (long long)u * lanes)
+                                                       : ld_keep(reinterpret_cast<const V *>(row2) + cv + (long long)u * lanes);
+#pragma unroll
+                        for (int k = 0; k < W; ++k) v[u].v[k] = w_mul(v[u].v[k], w.v[k]);
+                    }
+                }
+                T x[U * W];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int k = 0; k < W; ++k) x[u * W + k] = v[u].v[k];
+                acc.push_batch(x);
+            }
+            for (; cv < c_hi; cv += lanes) {
+                V v = ld_stream(reinterpret_cast<const V *>(row) + cv);
+                if constexpr (LOADER == LD_MUL || LOADER == LD_MATVEC) {
+                    const V w = ld_keep(reinterpret_cast<const V *>(row2) + cv);
+#pragma unroll
+                    for (int k = 0; k < W; ++k) v.v[k] = w_mul(v.v[k], w.v[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < W; ++k) acc.push(v.v[k]);
+            }
+        }
+    } else {
+        acc.init((T)0);
+    }
+    warp_merge(acc);
+    if (lanes == 32) {
+        if (active && lane == 0) emit(acc, out, partial, o, s, G.nout, G.S, G.fin, divisor, flag);
+        return;
+    }
+    // block per output: merge the eight warp results in warp order
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) smem[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0 && active) {
+        Acc<T, KIND> t = smem[0];
+#pragma unroll
+        for (int w = 1; w < kThreads / 32; ++w) t.merge(smem[w]);
+        emit(t, out, partial, o, s, G.nout, G.S, G.fin, divisor, flag);
+    }
+}
+
+// ---- generic: any number of groups, a block per output ------------------------------------------------------
+struct GenericGeom {
+    int nk, nr;
+    long long kext[FEO_MAX_RANK], kstr[FEO_MAX_RANK], rext[FEO_MAX_RANK], rstr[FEO_MAX_RANK];
+    long long nout, nred;
+    int fin;
+};
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kThreads) reduce_generic_kernel(T *__restrict__ out, const T *__restrict__ in,
+                                                                  const T *__restrict__ aux, const __grid_constant__ GenericGeom G,
+                                                                  T divisor, int *flag) {
+    __shared__ Acc<T, KIND> smem[kThreads / 32];
+    for (long long o = blockIdx.x; o < G.nout; o += gridDim.x) {
+        long long rem = o, base = 0;
+#pragma unroll 1
+        for (int d = G.nk - 1; d >= 0; --d) { base += (rem % G.kext[d]) * G.kstr[d]; rem /= G.kext[d]; }
+        Acc<T, KIND> acc;
+        acc.init(aux_val<KIND>(aux, o));
+        for (long long i = threadIdx.x; i < G.nred; i += kThreads) {
+            long long q = i, off = base;
+#pragma unroll 1
+            for (int d = G.nr - 1; d >= 0; --d) { off += (q % G.rext[d]) * G.rstr[d]; q /= G.rext[d]; }
+            acc.push(__ldg(in + off));
+        }
+        warp_merge(acc);
+        if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Acc<T, KIND> t = smem[0];
+#pragma unroll
+            for (int w = 1; w < kThreads / 32; ++w) t.merge(smem[w]);
+            finalize(t, out, o, G.nout, G.fin, divisor, flag);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- stage 2: merge S partial accumulators per output, in split order ------------------------------------------
+template <typename T, int KIND, bool WARP>
+__global__ void __launch_bounds__(kThreads) reduce_stage2_kernel(T *__restrict__ out, const void *__restrict__ partial,
+                                                                 long long nout, long long S, int fin, T divisor, int *flag) {
+    const Acc<T, KIND> *p = reinterpret_cast<const Acc<T, KIND> *>(partial);
+    if constexpr (WARP) {
+        const long long o = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+        const int lane = threadIdx.x & 31;
+        if (o >= nout) return;
+        Acc<T, KIND> acc;
+        acc.init((T)0);
+        if constexpr (KIND == K_SQDEV) acc.m = p[o].m;
+        // each lane takes a contiguous run of splits; the order is fixed, so results are deterministic
+        const long long per = (S + 31) / 32;
+        const long long lo = lane * per, hi = (lo + per < S) ? lo + per : S;
+        for (long long s = lo; s < hi; ++s) acc.merge(p[s * nout + o]);
+        warp_merge(acc);
+        if (lane == 0) finalize(acc, out, o, nout, fin, divisor, flag);
+    } else {
+        const long long o = (long long)blockIdx.x * kThreads + threadIdx.x;
+        if (o >= nout) return;
+        Acc<T, KIND> acc = p[o];
+        for (long long s = 1; s < S; ++s) acc.merge(p[s * nout + o]);
+        finalize(acc, out, o, nout, fin, divisor, flag);
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------
+struct Canon {
+    bool ok;  // fits the canonical 4-group form
+    long long K1, R1, K2, R2;
+};
+
+// groups: extents with their reduced flag, alternating, outermost first
+inline Canon canonicalise(int m, const long long *ext, const bool *red) {
+    Canon c{true, 1, 1, 1, 1};
+    if (m == 0) return c;
+    if (red[m - 1]) {
+        if (m > 4) { c.ok = false; return c; }
+        c.R2 = ext[m - 1];
+        if (m >= 2) c.K2 = ext[m - 2];
+        if (m >= 3) c.R1 = ext[m - 3];
+        if (m >= 4) c.K1 = ext[m - 4];
+    } else {
+        if (m > 3) { c.ok = false; return c; }
+        c.K2 = ext[m - 1];
+        if (m >= 2) c.R1 = ext[m - 2];
+        if (m >= 3) c.K1 = ext[m - 3];
+    }
+    return c;
+}
+
+inline long long clampll(long long v, long long lo, long long hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// Runs one canonical reduction.  `in2`: second operand for the dot-like loaders; `aux`: per-output mean (K_SQDEV).
+template <typename T, int KIND, int LOADER>
+int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in2, const T *aux, int fin, T divisor) {
+    constexpr int VN = VecN<T>::value;
+    Geom G;
+    memset(&G, 0, sizeof G);
+    G.K1 = c.K1; G.R1 = c.R1; G.K2 = c.K2; G.R2 = c.R2;
+    G.nout = c.K1 * c.K2;
+    G.fin = fin;
+    G.S = G.S1 = G.S2 = 1;
+    G.lanes = 32;
+    const long long target_blocks = (long long)ctx->sm_count * (ctx->knobs[FEO_KNOB_REDUCE_BLOCKS_PER_SM] > 0 ? ctx->knobs[FEO_KNOB_REDUCE_BLOCKS_PER_SM] : 8);
+    const int forced = ctx->knobs[FEO_KNOB_REDUCE_SPLIT];
+    const bool in_aligned = feo_aligned16(in) && (LOADER == LD_PLAIN || LOADER == LD_VECMAT || feo_aligned16(in2));
+    enum { COLS, MICRO, ROWS } which;
+    bool vec = false;
+    int r2c = 0;
+
+    if (c.R2 == 1 && LOADER != LD_MUL && LOADER != LD_MATVEC) {
+        which = COLS;
+        vec = in_aligned && (c.K2 % VN == 0);
+        const long long W = vec ? VN : 1;
+        G.xblocks = feo_ceil_div((size_t)(c.K2 / W), (size_t)kThreads);
+        const long long base_blocks = G.xblocks * c.K1;
+        long long S = forced > 0 ? forced : feo_ceil_div((size_t)target_blocks, (size_t)base_blocks);
+        S = clampll(S, 1, c.R1 >= 32 ? c.R1 / 16 : 1);
+        G.c1 = feo_ceil_div((size_t)c.R1, (size_t)S);
+        G.S = G.S1 = feo_ceil_div((size_t)c.R1, (size_t)G.c1);
+    } else if (c.R2 <= 32 && LOADER == LD_PLAIN) {
+        which = MICRO;
+        const int cands[5] = {2, 4, 8, 16, 32};
+        for (int i = 0; i < 5; ++i)
+            if (c.R2 == cands[i] && feo_aligned16(in)) r2c = cands[i];
+        G.xblocks = feo_ceil_div((size_t)c.K2, (size_t)kThreads);
+        const long long base_blocks = G.xblocks * c.K1;
+        long long S = forced > 0 ? forced : feo_ceil_div((size_t)target_blocks, (size_t)base_blocks);
+        S = clampll(S, 1, c.R1 >= 32 ? c.R1 / 16 : 1);
+        G.c1 = feo_ceil_div((size_t)c.R1, (size_t)S);
+        G.S = G.S1 = feo_ceil_div((size_t)c.R1, (size_t)G.c1);
+    } else {
+        which = ROWS;
+        vec = in_aligned && (c.R2 % VN == 0);
+        const long long W = vec ? VN : 1;
+        const long long nvec = c.R2 / W;
+        const long long per_out = c.R1 * c.R2;
+        G.lanes = (per_out >= 4096) ? kThreads : 32;
+        const long long outs_per_block = kThreads / G.lanes;
+        const long long base_blocks = feo_ceil_div((size_t)G.nout, (size_t)outs_per_block);
+        long long S = forced > 0 ? forced : feo_ceil_div((size_t)target_blocks, (size_t)base_blocks);
+        const long long min_elems = 16384;  // keep at least 64 KiB (f32) of work per split
+        S = clampll(S, 1, per_out / min_elems > 0 ? per_out / min_elems : 1);
+        // split rows first, then columns
+        long long S1 = S < c.R1 ? S : c.R1;
+        G.c1 = feo_ceil_div((size_t)c.R1, (size_t)S1);
+        S1 = feo_ceil_div((size_t)c.R1, (size_t)G.c1);
+        long long S2 = feo_ceil_div((size_t)S, (size_t)S1);
+        const long long quantum = (long long)G.lanes * 4;  // U vectors per lane per sweep
+        long long c2 = feo_ceil_div((size_t)nvec, (size_t)S2);
+        c2 = feo_ceil_div((size_t)c2, (size_t)quantum) * quantum;
+        S2 = feo_ceil_div((size_t)nvec, (size_t)c2);
+        G.S1 = S1; G.S2 = S2; G.S = S1 * S2; G.c2 = c2;
+    }
+
+    void *partial = nullptr;
+    if (G.S > 1) {
+        int rc = feo_workspace(ctx, (size_t)G.S * (size_t)G.nout * sizeof(Acc<T, KIND>), &partial);
+        if (rc != FEO_OK) return rc;
+    }
+    int *flag = ctx->arith_flag;
+    if (which == COLS) {
+        const long long blocks = G.xblocks * G.S * c.K1;
+        if (blocks > 0x7fffffffLL) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "reduction grid too large");
+        constexpr int L = (LOADER == LD_VECMAT) ? LD_VECMAT : LD_PLAIN;
+        if (vec) reduce_cols_kernel<T, KIND, L, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
+        else reduce_cols_kernel<T, KIND, L, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
+    } else if (which == MICRO) {
+        const long long blocks = G.xblocks * G.S * c.K1;
+        if (blocks > 0x7fffffffLL) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "reduction grid too large");
+#define FEO_MICRO(R) reduce_micro_kernel<T, KIND, R><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, aux, G, divisor, flag)
+        switch (r2c) {
+        case 2: FEO_MICRO(2); break;
+        case 4: FEO_MICRO(4); break;
+        case 8: FEO_MICRO(8); break;
+        case 16: FEO_MICRO(16); break;
+        case 32: FEO_MICRO(32); break;
+        default: FEO_MICRO(0); break;
+        }
+#undef FEO_MICRO
+    } else {
+        const long long units = G.nout * G.S;
+        const long long blocks = feo_ceil_div((size_t)units, (size_t)(kThreads / G.lanes));
+        if (blocks > 0x7fffffffLL) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "reduction grid too large");
+        constexpr int L = (LOADER == LD_MUL || LOADER == LD_MATVEC) ? LOADER : LD_PLAIN;
+        if (vec) reduce_rows_kernel<T, KIND, L, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
+        else reduce_rows_kernel<T, KIND, L, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
+    }
+    FEO_LAUNCH_CHECK(ctx);
+    if (G.S > 1) {
+        if (G.nout < 4096) {
+            const long long blocks = feo_ceil_div((size_t)G.nout * 32, (size_t)kThreads);
+            reduce_stage2_kernel<T, KIND, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, G.nout, G.S, fin, divisor, flag);
+        } else {
+            const long long blocks = feo_ceil_div((size_t)G.nout, (size_t)kThreads);
+            reduce_stage2_kernel<T, KIND, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, G.nout, G.S, fin, divisor, flag);
+        }
+        FEO_LAUNCH_CHECK(ctx);
+    }
+    return FEO_OK;
+}
+
+}  // namespace feo_red

@@ -1,0 +1,176 @@
+/* feotensor_b200.h -- C ABI of libfeotensor_b200.so, the B200-native compute backend for the
+ * feotensor hot path (elementwise operators, axis reductions, outer product, dot, matmul).
+ *
+ * The reference (Rust crate feotensor) has NO plugin / FFI seam: its only boundary is the public
+ * Rust API on concrete types whose storage field is private (tensor.rs:15-18).  This header is the
+ * boundary a `DeviceStorage<T>` placed beside `DynamicStorage<T>` (storage.rs:7-10) binds with
+ * `extern "C"`; every entry point names the reference function it replaces (file:line relative to
+ * the reference's src/).  INTEGRATION.md shows the Rust-side binding.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; device pointers are raw CUDA device addresses (void*), dense
+ *    row-major exactly like DynamicStorage::flatten (storage.rs:18-38);
+ *  - every call returns a feo_status; the text of the last failure is feo_last_error(ctx);
+ *    FEO_ERR_SHAPE covers the reference's ShapeError cases AND the preconditions the reference
+ *    panics on (operator shape mismatch tensor.rs:366, inner-dimension mismatch matrix.rs:78,
+ *    axes that are not strictly ascending / in range -- SURVEY.md 8a-quirks);
+ *  - compute calls are asynchronous on the context's CUDA stream; feo_download and feo_sync are
+ *    the synchronisation points; one host thread per context;
+ *  - there is NO CPU fallback: without a CUDA device feo_init fails with FEO_ERR_CUDA.
+ */
+#ifndef FEOTENSOR_B200_H
+#define FEOTENSOR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FEO_API __attribute__((visibility("default")))
+#else
+#define FEO_API
+#endif
+
+#define FEO_MAX_RANK 8
+#define FEO_ABI_VERSION 1
+
+typedef struct feo_ctx feo_ctx;
+
+typedef enum {
+    FEO_OK = 0,
+    FEO_ERR_SHAPE = 1,       /* ShapeError (error.rs:3-20) or a reference panic precondition */
+    FEO_ERR_CUDA = 2,        /* CUDA runtime / driver failure, or no device */
+    FEO_ERR_UNSUPPORTED = 3, /* dtype / algorithm / rank not supported by this build */
+    FEO_ERR_ARITH = 4        /* reserved: integer /0 or MIN/-1 is reported through feo_arith_flag */
+} feo_status;
+
+/* Element types: any `T: Num + PartialOrd + Copy` primitive the reference admits (tensor.rs:21). */
+typedef enum { FEO_F32 = 0, FEO_F64 = 1, FEO_I32 = 2, FEO_I64 = 3, FEO_U32 = 4 } feo_dtype;
+
+/* std::ops::{Add, Sub, Mul, Div} (tensor.rs:336-489). */
+typedef enum { FEO_ADD = 0, FEO_SUB = 1, FEO_MUL = 2, FEO_DIV = 3 } feo_op;
+
+/* Tensor::{sum, mean, var, max, min} (tensor.rs:70-307). */
+typedef enum { FEO_SUM = 0, FEO_MEAN = 1, FEO_VAR = 2, FEO_MAX = 3, FEO_MIN = 4 } feo_reduce_kind;
+
+/* Matrix::matmul algorithms.  AUTO = TF32X3 for f32 when the shape allows it, else SIMT. */
+typedef enum { FEO_MATMUL_AUTO = 0, FEO_MATMUL_SIMT = 1, FEO_MATMUL_TF32X3 = 2 } feo_matmul_algo;
+
+/* ---- context, stream, memory ------------------------------------------------------------------ */
+FEO_API int feo_abi_version(void);
+FEO_API size_t feo_dtype_size(int dtype);
+/* Creates a context on CUDA device `device` with its own non-blocking stream. */
+FEO_API int feo_init(int device, feo_ctx **ctx);
+FEO_API int feo_shutdown(feo_ctx *ctx);
+FEO_API const char *feo_last_error(feo_ctx *ctx);
+/* Adopt a caller-owned cudaStream_t (e.g. the host framework's current stream); NULL restores the
+ * context's own stream. */
+FEO_API int feo_set_stream(feo_ctx *ctx, void *cuda_stream);
+FEO_API void *feo_get_stream(feo_ctx *ctx);
+FEO_API int feo_sync(feo_ctx *ctx);
+/* Number of kernels this context has launched since feo_init (monotonic). */
+FEO_API uint64_t feo_launch_count(feo_ctx *ctx);
+/* Tuning knobs for experiments; unknown knobs return FEO_ERR_UNSUPPORTED. */
+FEO_API int feo_tune(feo_ctx *ctx, int knob, int value);
+
+/* Stream-ordered device allocation: the storage behind DeviceStorage<T> (replaces the Vec<T> of
+ * DynamicStorage, storage.rs:7-15). */
+FEO_API int feo_malloc(feo_ctx *ctx, size_t bytes, void **dptr);
+FEO_API int feo_free(feo_ctx *ctx, void *dptr);
+/* Pinned host staging buffers for uploads / downloads. */
+FEO_API int feo_host_alloc(feo_ctx *ctx, size_t bytes, void **hptr);
+FEO_API int feo_host_free(feo_ctx *ctx, void *hptr);
+/* Tensor::new copies host data in (tensor.rs:22-30): asynchronous H2D on the context stream. */
+FEO_API int feo_upload(feo_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+/* Reads results back (the reference hands out &T / iterators, storage.rs:40-100): D2H, then waits. */
+FEO_API int feo_download(feo_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+/* D2H without the wait (pair with feo_sync). */
+FEO_API int feo_download_async(feo_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+FEO_API int feo_copy(feo_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes);
+
+/* ---- bookkeeping (host-only, exact integer logic) --------------------------------------------- */
+/* Shape::new (shape.rs:12-17): FEO_ERR_SHAPE if any dimension is zero; rank 0 is allowed. */
+FEO_API int feo_shape_check(int rank, const size_t *shape);
+/* Shape::size (shape.rs:19-21). */
+FEO_API size_t feo_shape_size(int rank, const size_t *shape);
+/* DynamicStorage::flatten (storage.rs:18-38).  Returns FEO_OK and *index, or FEO_ERR_SHAPE with
+ * *detail = -1 for an order mismatch (:19-22) or the first out-of-bounds dimension (:24-30). */
+FEO_API int feo_flatten(int coord_rank, const size_t *coord, int rank, const size_t *shape, size_t *index, int *detail);
+/* Result shape of a reduction: kept dims ascending (tensor.rs:72-80); [1] when axes is empty or
+ * nothing is kept (tensor.rs:84-87).  FEO_ERR_SHAPE unless axes are strictly ascending and in range. */
+FEO_API int feo_reduce_shape(int rank, const size_t *shape, int naxes, const size_t *axes, int *out_rank, size_t *out_shape);
+/* The divisor `n` of mean / var, built in type T by counting (tensor.rs:112-130, :136-155), in
+ * closed form.  *out is one element of `dtype`. */
+FEO_API int feo_reduce_divisor(int dtype, int rank, const size_t *shape, int naxes, const size_t *axes, void *out);
+
+/* ---- constructors ----------------------------------------------------------------------------- */
+/* Tensor::fill / zeros / ones (tensor.rs:32-44): `value` points at one host element of dtype. */
+FEO_API int feo_fill(feo_ctx *ctx, int dtype, void *out, const void *value, size_t n);
+/* Matrix::eye (matrix.rs:36-42): zeros, then ones on (i, i) for i < rows; FEO_ERR_SHAPE if rows > cols
+ * (the reference panics through an out-of-bounds set). */
+FEO_API int feo_eye(feo_ctx *ctx, int dtype, void *out, size_t rows, size_t cols);
+
+/* Synthetic data for benchmarks and full-size parity checks (no reference counterpart): element i
+ * gets a value that depends only on (seed, first_index + i) -- a counter-based generator, so sharded
+ * and unsharded runs see identical data and the host can regenerate any element.  Floats: uniform in
+ * [lo, hi); integers: uniform in [lo, hi) with hi > lo.  oracle/feo_oracle.c holds the host twin. */
+FEO_API int feo_fill_uniform(feo_ctx *ctx, int dtype, void *out, size_t n, uint64_t seed, uint64_t first_index, double lo, double hi);
+
+/* ---- elementwise operators -------------------------------------------------------------------- */
+/* Add/Sub/Mul/Div<Tensor<T>> for Tensor<T> (tensor.rs:362-373, 405-416, 435-446, 478-489):
+ * out[i] = a[i] op b[i], i < n.  The caller has checked shape equality (the reference asserts). */
+FEO_API int feo_ewise(feo_ctx *ctx, int op, int dtype, void *out, const void *a, const void *b, size_t n);
+/* Add/Sub/Mul/Div<T> for Tensor<T> (tensor.rs:336-359, 392-402, 465-475): out[i] = a[i] op *scalar. */
+FEO_API int feo_ewise_scalar(feo_ctx *ctx, int op, int dtype, void *out, const void *a, const void *scalar_host, size_t n);
+/* Broadcasting elementwise (NEW surface): out is dense row-major of `shape`;
+ * a_strides / b_strides are element strides of the operands viewed at `shape`, 0 = broadcast.
+ * Semantics: materialise both operands, then the reference operator. */
+FEO_API int feo_ewise_broadcast(feo_ctx *ctx, int op, int dtype, void *out, const void *a, const void *b, int rank,
+                        const size_t *shape, const size_t *a_strides, const size_t *b_strides);
+/* Sticky per-context flag set when an integer kernel met x/0 or MIN/-1 (the reference panics; the
+ * kernel writes 0 there).  *flag receives it; clear != 0 resets it.  Synchronises the stream. */
+FEO_API int feo_arith_flag(feo_ctx *ctx, int *flag, int clear);
+
+/* ---- reductions ------------------------------------------------------------------------------- */
+/* Tensor::sum / mean / var / max / min (tensor.rs:70-108, 110-132, 134-203, 205-255, 257-307).
+ * `in` is dense row-major of `shape`; `out` has feo_reduce_shape elements.  Floats: tree order
+ * (reassociation-bounded vs the reference's sequential order), var by Welford/Chan in one pass;
+ * integers: bit-exact, var by the reference's own two-pass integer scheme. */
+FEO_API int feo_reduce(feo_ctx *ctx, int kind, int dtype, void *out, const void *in, int rank, const size_t *shape,
+               int naxes, const size_t *axes);
+/* Building blocks for a tensor sharded on its leading axis:
+ *  SUM/MEAN -> per-shard sums, MAX/MIN -> per-shard extrema (combine with an all-reduce);
+ *  VAR (floats) -> out holds nout means followed by nout M2 values (combine with feo_var_merge). */
+FEO_API int feo_reduce_partial(feo_ctx *ctx, int kind, int dtype, void *out, const void *in, int rank,
+                       const size_t *shape, int naxes, const size_t *axes);
+/* Chan merge of `nparts` equal-count partials laid out [part][mean x nout | M2 x nout], then the
+ * division by *divisor_host (one element of dtype): out[o] = M2_total[o] / n. */
+FEO_API int feo_var_merge(feo_ctx *ctx, int dtype, void *out, const void *partials, size_t nparts, size_t nout,
+                  size_t count_per_part, const void *divisor_host);
+/* Second pass of the integer variance (tensor.rs:196-198): out[o] = sum over the removed axes of
+ * (x - mean[o])^2, no division. */
+FEO_API int feo_reduce_sqdev(feo_ctx *ctx, int dtype, void *out, const void *in, const void *mean, int rank,
+                     const size_t *shape, int naxes, const size_t *axes);
+
+/* ---- products --------------------------------------------------------------------------------- */
+/* Tensor::prod (tensor.rs:311-322): out[i * nb + j] = a[i] * b[j]. */
+FEO_API int feo_outer(feo_ctx *ctx, int dtype, void *out, const void *a, size_t na, const void *b, size_t nb);
+/* DynamicVector::vecmul (vector.rs:71-78): *out = sum_i a[i] * b[i] (one device element). */
+FEO_API int feo_dot(feo_ctx *ctx, int dtype, void *out, const void *a, const void *b, size_t n);
+/* `batch` independent dots of length n over row-major [batch, n] operands (BASELINE config 5). */
+FEO_API int feo_dot_batched(feo_ctx *ctx, int dtype, void *out, const void *a, const void *b, size_t batch, size_t n);
+/* DynamicMatrix::vecmul (matrix.rs:92-103): out[i] = sum_j A[i,j] * v[j];  A is [M, K]. */
+FEO_API int feo_matvec(feo_ctx *ctx, int dtype, void *out, const void *A, const void *v, size_t M, size_t K);
+/* DynamicVector::matmul (vector.rs:80-91): out[j] = sum_i v[i] * A[i,j];  A is [K, N]. */
+FEO_API int feo_vecmat(feo_ctx *ctx, int dtype, void *out, const void *v, const void *A, size_t K, size_t N);
+/* DynamicMatrix::matmul (matrix.rs:76-90): C[M,N] = A[M,K] * B[K,N], all row-major.  The caller has
+ * checked A.cols == B.rows (the reference assert_eq!s, matrix.rs:78). */
+FEO_API int feo_matmul(feo_ctx *ctx, int algo, int dtype, void *C, const void *A, const void *B, size_t M, size_t K, size_t N);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEOTENSOR_B200_H */

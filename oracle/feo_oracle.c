@@ -280,3 +280,32 @@ int feo_oracle_matmul_entries(int dtype, void *out, const void *A, const void *B
     DISPATCH(dtype, CALL)
 #undef CALL
 }
+
+/* Host twin of the library's synthetic-data generator (feo_fill_uniform in include/feotensor_b200.h):
+ * element i = f(seed, first_index + i).  Not part of the reference; it lets tests regenerate any
+ * element of a full-size device tensor without downloading it. */
+static inline uint64_t oracle_mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+int feo_oracle_fill_uniform(int dtype, void *out, size_t n, uint64_t seed, uint64_t first_index, size_t stride,
+                            double lo, double hi) {
+    /* writes n elements, element k taken at global index first_index + k * stride */
+    for (size_t k = 0; k < n; ++k) {
+        const uint64_t h = oracle_mix64(seed * 0xD1342543DE82EF95ULL + (first_index + (uint64_t)k * stride));
+        switch (dtype) {
+        case 0: { const float l = (float)lo, span = (float)((float)hi - (float)lo);
+                  const float u = (float)(h >> 40) * (1.0f / 16777216.0f);
+                  const float m = span * u; ((float *)out)[k] = l + m; break; }
+        case 1: { const double span = hi - lo; const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+                  const double m = span * u; ((double *)out)[k] = lo + m; break; }
+        case 2: { const uint64_t r = (uint64_t)((int64_t)hi - (int64_t)lo); ((int32_t *)out)[k] = (int32_t)((uint32_t)(int32_t)lo + (uint32_t)(h % r)); break; }
+        case 3: { const uint64_t r = (uint64_t)((int64_t)hi - (int64_t)lo); ((int64_t *)out)[k] = (int64_t)((uint64_t)(int64_t)lo + (h % r)); break; }
+        case 4: { const uint64_t r = (uint64_t)((int64_t)hi - (int64_t)lo); ((uint32_t *)out)[k] = (uint32_t)lo + (uint32_t)(h % r); break; }
+        default: return ORACLE_ERR_UNSUPPORTED;
+        }
+    }
+    return ORACLE_OK;
+}

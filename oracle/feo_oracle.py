@@ -281,3 +281,12 @@ def matmul_entries(A, B, rows, cols):
                                          C.c_size_t(A.shape[1]), C.c_size_t(B.shape[1]), _p(rows), _p(cols),
                                          C.c_size_t(rows.size)), "matmul_entries")
     return out
+
+
+# ---- synthetic data (twin of the library's feo_fill_uniform; not part of the reference) --------------
+def fill_uniform(dtype: str, n: int, seed: int, first_index: int = 0, lo: float = -1.0, hi: float = 1.0, stride: int = 1):
+    """Elements first_index, first_index + stride, ... of the counter-based stream `seed`."""
+    out = np.empty(n, NP_DTYPES[dtype])
+    _chk(lib().feo_oracle_fill_uniform(DTYPES[dtype], _p(out), C.c_size_t(n), C.c_uint64(seed), C.c_uint64(first_index),
+                                       C.c_size_t(stride), C.c_double(lo), C.c_double(hi)), "fill_uniform")
+    return out

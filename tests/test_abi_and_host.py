@@ -1,0 +1,132 @@
+"""CPU-side checks of the boundary: the C-ABI library loads here (no GPU) and exports every symbol
+include/feotensor_b200.h declares; host-only bookkeeping entry points agree with the oracle and the
+reference's golden vectors; the product fails loudly without a device and never touches the oracle.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "feotensor_b200.h")).read()
+    return sorted(set(re.findall(r"FEO_API[^;(]*?\b(feo_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_is_built_in_tree():
+    import feotensor_b200
+    assert os.path.exists(feotensor_b200.LIB_PATH), "run __graft_entry__.build()"
+    assert feotensor_b200.LIB_PATH.startswith(ROOT)
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    import feotensor_b200._lib as L
+    lib = L.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in L.SIGNATURES, f"{name} has no ctypes prototype"
+    assert sorted(L.SIGNATURES) == declared
+    assert lib.feo_abi_version() == 1
+    assert [lib.feo_dtype_size(i) for i in range(5)] == [4, 8, 4, 8, 4]
+
+
+def test_library_is_sm100a_and_uses_no_cpu_fallback():
+    import feotensor_b200
+    out = subprocess.run(["cuobjdump", "--list-elf", feotensor_b200.LIB_PATH], capture_output=True, text=True)
+    if out.returncode == 0:
+        assert "sm_100a" in out.stdout
+        assert not re.search(r"sm_(?!100a)\d+", out.stdout)
+    # the product never links or loads the oracle
+    ldd = subprocess.run(["ldd", feotensor_b200.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd
+    for fn in os.listdir(os.path.join(ROOT, "feotensor_b200")):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(ROOT, "feotensor_b200", fn)).read().replace("no oracle", "").replace(
+                "imports the oracle", "").replace("import the oracle", ""), fn
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="only meaningful on a box without a GPU")
+def test_no_device_means_loud_failure():
+    import feotensor_b200 as f
+    with pytest.raises(f.BackendError):
+        f.Context(0)
+    with pytest.raises(f.BackendError):
+        f.Tensor(f.shape(2), [1.0, 2.0])
+
+
+def test_host_bookkeeping_matches_reference_kats(kat, oracle):
+    import feotensor_b200 as f
+    for c in kat:
+        op = c["op"]
+        if op == "shape_new":
+            assert f.Shape(c["dims"]).dims == c["dims"]
+        elif op == "shape_new_err":
+            with pytest.raises(f.ShapeError):
+                f.Shape(c["dims"])
+        elif op == "shape_size":
+            assert f.Shape(c["dims"]).size() == c["size"]
+        elif op == "shape_display":
+            assert str(f.Shape(c["dims"])) == c["text"]
+        elif op == "shape_stack":
+            assert f.Shape(c["a"]).stack(f.Shape(c["b"])).dims == c["expect"]
+        elif op == "coord_order":
+            assert f.Coordinate(c["indices"]).order() == c["order"]
+        elif op == "coord_insert":
+            assert f.Coordinate(c["indices"]).insert(c["index"], c["value"]) == f.Coordinate(c["expect"])
+        elif op == "coord_display":
+            assert str(f.Coordinate(c["indices"])) == c["text"]
+        elif op == "index_iterator":
+            assert [list(x) for x in f.IndexIterator(f.Shape(c["dims"]))] == c["expect"]
+    # coordinate.rs:12-15, coord! repeat form
+    with pytest.raises(f.ShapeError):
+        f.Coordinate([])
+    assert f.coord(1, count=3) == f.Coordinate([1, 1, 1])
+    assert str(f.ShapeError("x")) == "ShapeError: x"
+
+
+def test_flatten_reduce_shape_divisor_match_oracle(oracle):
+    import feotensor_b200._lib as L
+    lib = L.load()
+    rng = np.random.default_rng(11)
+    for _ in range(200):
+        rank = int(rng.integers(1, 6))
+        shape = [int(x) for x in rng.integers(1, 6, rank)]
+        coord = [int(rng.integers(0, s + 1)) for s in shape]  # sometimes out of bounds
+        idx, detail = C.c_size_t(0), C.c_int(0)
+        rc = lib.feo_flatten(rank, L.sizes(coord), rank, L.sizes(shape), C.byref(idx), C.byref(detail))
+        orc, oidx = oracle.flatten(coord, shape)
+        assert (rc == 0) == (orc == 0)
+        if rc == 0:
+            assert idx.value == oidx
+        else:
+            assert detail.value == orc - 2
+        naxes = int(rng.integers(0, rank + 1))
+        axes = sorted(rng.choice(rank, naxes, replace=False).tolist())
+        out_rank, out_shape = C.c_int(0), (C.c_size_t * 8)()
+        assert lib.feo_reduce_shape(rank, L.sizes(shape), naxes, L.sizes(axes), C.byref(out_rank), out_shape) == 0
+        assert tuple(out_shape[i] for i in range(out_rank.value)) == oracle.reduce_shape(shape, axes)
+    # order mismatch
+    idx, detail = C.c_size_t(0), C.c_int(0)
+    assert lib.feo_flatten(3, L.sizes([0, 0, 0]), 2, L.sizes([2, 2]), C.byref(idx), C.byref(detail)) == L.ERR_SHAPE
+    assert detail.value == -1
+    # bad axes are refused (the reference panics)
+    out_rank, out_shape = C.c_int(0), (C.c_size_t * 8)()
+    for bad in ([2, 0], [1, 1], [3]):
+        assert lib.feo_reduce_shape(3, L.sizes([2, 3, 4]), len(bad), L.sizes(bad), C.byref(out_rank), out_shape) == L.ERR_SHAPE
+    # the counting divisor in closed form == the oracle's literal counting loop
+    cases = [("f32", (16384, 16384, 8), [0, 1, 2]), ("f32", (2 ** 25,), []), ("f32", (2 ** 24 + 7, 3), [0]),
+             ("f64", (2 ** 20, 5), [0, 1]), ("i32", (70000, 70000), [0, 1]), ("u32", (2 ** 20, 2 ** 13), [0, 1]),
+             ("i64", (2 ** 20, 2 ** 13), []), ("f32", (64, 128, 256), [0, 2])]
+    for dt, shape, axes in cases:
+        out = np.zeros(1, oracle.NP_DTYPES[dt])
+        assert lib.feo_reduce_divisor(L.code_of(dt), len(shape), L.sizes(shape), len(axes), L.sizes(axes),
+                                      out.ctypes.data_as(C.c_void_p)) == 0
+        assert out[0] == oracle.reduce_divisor(dt, shape, axes), (dt, shape, axes)

@@ -1,0 +1,494 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (via the reference-API mirror), against
+the CPU oracle on the same inputs and against the reference's golden vectors.
+
+Bar (BASELINE.json north_star): bit-exact for integer dtypes, elementwise ops, outer product,
+max/min and all shape bookkeeping; float sum/mean/var/dot/matmul within the reassociation bound
+    |gpu - ref| <= 2 * gamma_n * sum|terms|,   gamma_n = n*u / (1 - n*u),  u = 2^-24 (f32) / 2^-53 (f64)
+(both summation orders are within gamma_n * sum|terms| of the exact sum).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FLOATS = ["f32", "f64"]
+INTS = ["i32", "i64", "u32"]
+ALL = FLOATS + INTS
+U = {"f32": 2.0 ** -24, "f64": 2.0 ** -53}
+
+
+@pytest.fixture(scope="module")
+def feo():
+    import feotensor_b200 as f
+    f.Context.default()  # raises without a GPU: these tests never fall back
+    return f
+
+
+def npdt(oracle, dt):
+    return oracle.NP_DTYPES[dt]
+
+
+def rand(oracle, rng, dt, shape, lo=-1.0, hi=1.0):
+    if dt in FLOATS:
+        return rng.uniform(lo, hi, shape).astype(npdt(oracle, dt))
+    lo_i, hi_i = (0, 2000) if dt == "u32" else (-1000, 1000)
+    return rng.integers(lo_i, hi_i, shape).astype(npdt(oracle, dt))
+
+
+def gamma(n, dt):
+    nu = n * U[dt]
+    assert nu < 1
+    return nu / (1 - nu)
+
+
+def assert_sum_like(got, ref, abs_terms_sum, n, dt, what=""):
+    """Reassociation bound for sums of n terms whose absolute values add up to abs_terms_sum."""
+    bound = 2 * gamma(n, dt) * np.asarray(abs_terms_sum, dtype=np.float64) + 1e-300
+    err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+    assert np.all(err <= bound), f"{what}: max err {err.max():.3e} bound {bound.flat[np.argmax(err - bound)]:.3e}"
+
+
+# ---- the reference's own known-answer tests, on the GPU ----------------------------------------------
+def _mk(feo, via, shape, data, dt):
+    if via == "vector":
+        return feo.Vector(data, dtype=dt)
+    if via == "matrix":
+        return feo.Matrix(feo.Shape(shape), data, dtype=dt)
+    return feo.Tensor(feo.Shape(shape), data, dtype=dt)
+
+
+def _ints_ok(*seqs):
+    return all(float(x).is_integer() for s in seqs for x in (s if isinstance(s, list) else [s]))
+
+
+def test_reference_kats_reductions(feo, kat, oracle):
+    n = 0
+    for c in [c for c in kat if c["op"] == "reduce"]:
+        dts = list(FLOATS)
+        if _ints_ok(c["data"], c["expect"]):
+            dts += ["i32", "i64"] + ([] if any(x < 0 for x in c["data"] + c["expect"]) else ["u32"])
+        for dt in dts:
+            x = _mk(feo, c["via"], c["shape"], c["data"], dt)
+            res = getattr(x, c["kind"])() if c["via"] == "vector" else getattr(x, c["kind"])(c["axes"])
+            assert res.shape().dims == c["expect_shape"], c["ref"]
+            np.testing.assert_array_equal(res.to_numpy().reshape(-1), np.array(c["expect"], npdt(oracle, dt)), err_msg=c["ref"] + dt)
+            n += 1
+    assert n > 100
+
+
+def test_reference_kats_elementwise(feo, kat, oracle):
+    for c in [c for c in kat if c["op"] in ("ewise", "ewise_scalar")]:
+        nums = c["a"] + c["expect"] + (c["b"] if c["op"] == "ewise" else [c["scalar"]])
+        dts = list(FLOATS)
+        if _ints_ok(nums):
+            dts += ["i32", "i64"] + ([] if any(x < 0 for x in nums) else ["u32"])
+        for dt in dts:
+            a = _mk(feo, c["lhs"], c["shape"], c["a"], dt)
+            b = _mk(feo, c["rhs"], c["shape"], c["b"], dt) if c["op"] == "ewise" else c["scalar"]
+            res = {"add": a + b, "sub": a - b, "mul": a * b, "div": a / b}[c["opname"]]
+            assert res.shape().dims == c["shape"], c["ref"]
+            np.testing.assert_array_equal(res.to_numpy().reshape(-1), np.array(c["expect"], npdt(oracle, dt)), err_msg=c["ref"] + dt)
+            # result newtype follows the reference's impl table (tensor.rs:375-505, matrix.rs:113-214, vector.rs:101-202)
+            want = c["lhs"] if c["lhs"] != "tensor" else (c["rhs"] if c["op"] == "ewise" else "tensor")
+            assert type(res).__name__.lower() == want, c["ref"]
+
+
+def test_reference_kats_products(feo, kat, oracle):
+    for dt in ALL:
+        T = npdt(oracle, dt)
+        for c in [c for c in kat if c["op"] == "prod"]:
+            a = feo.Tensor(feo.Shape(c["a_shape"]), c["a"], dtype=dt)
+            b = feo.Tensor(feo.Shape(c["b_shape"]), c["b"], dtype=dt)
+            r = a.prod(b)
+            assert r.shape().dims == c["expect_shape"]
+            np.testing.assert_array_equal(r.to_numpy().reshape(-1), np.array(c["expect"], T), err_msg=c["ref"])
+        for c in [c for c in kat if c["op"] == "matmul"]:
+            A = feo.Matrix(feo.Shape(c["a_shape"]), c["a"], dtype=dt)
+            B = feo.Matrix(feo.Shape(c["b_shape"]), c["b"], dtype=dt)
+            r = A.matmul(B)
+            assert r.shape().dims == c["expect_shape"]
+            np.testing.assert_array_equal(r.to_numpy().reshape(-1), np.array(c["expect"], T), err_msg=c["ref"])
+        for c in [c for c in kat if c["op"] == "matvec"]:
+            r = feo.Matrix(feo.Shape(c["a_shape"]), c["a"], dtype=dt).vecmul(feo.Vector(c["v"], dtype=dt))
+            assert r.shape().dims == c["expect_shape"]
+            np.testing.assert_array_equal(r.to_numpy(), np.array(c["expect"], T), err_msg=c["ref"])
+        for c in [c for c in kat if c["op"] == "vecmat"]:
+            r = feo.Vector(c["v"], dtype=dt).matmul(feo.Matrix(feo.Shape(c["a_shape"]), c["a"], dtype=dt))
+            np.testing.assert_array_equal(r.to_numpy(), np.array(c["expect"], T), err_msg=c["ref"])
+        for c in [c for c in kat if c["op"] == "dot"]:
+            r = feo.Vector(c["a"], dtype=dt).vecmul(feo.Vector(c["b"], dtype=dt))
+            assert r.shape().dims == c["expect_shape"]
+            np.testing.assert_array_equal(r.to_numpy(), np.array(c["expect"], T), err_msg=c["ref"])
+
+
+def test_reference_kats_constructors_and_access(feo, kat, oracle):
+    for c in kat:
+        op = c["op"]
+        if op == "new":
+            t = feo.Tensor(feo.Shape(c["shape"]), c["data"])
+            assert t.shape() == feo.Shape(c["shape"])
+            np.testing.assert_array_equal(t.data.to_numpy(), np.array(c["data"]))
+        elif op == "new_err":
+            with pytest.raises(feo.ShapeError):
+                feo.Tensor(feo.Shape(c["shape"]), c["data"])
+        elif op == "fill":
+            cls = {"tensor": feo.Tensor, "matrix": feo.Matrix, "vector": feo.Vector}[c.get("via", "tensor")]
+            t = getattr(cls, c["ctor"])(feo.Shape(c["shape"]), c["value"], dtype=c["dtype"]) if c["ctor"] == "fill" else \
+                getattr(cls, c["ctor"])(feo.Shape(c["shape"]), dtype=c["dtype"])
+            assert t.shape().dims == c["shape"] and t.size() == int(np.prod(c["shape"]))
+            np.testing.assert_array_equal(t.to_numpy().reshape(-1), np.full(t.size(), c["value"], npdt(oracle, c["dtype"])))
+        elif op == "eye":
+            np.testing.assert_array_equal(feo.Matrix.eye(feo.Shape(c["shape"])).to_numpy().reshape(-1), np.array(c["expect"]))
+        elif op == "get":
+            t = feo.Tensor(feo.Shape(c["shape"]), c["data"])
+            for co, want in zip(c["coords"], c["expect"]):
+                assert t.get(feo.Coordinate(co)) == want
+        elif op == "set":
+            t = feo.Tensor(feo.Shape(c["shape"]), c["data"])
+            for co, v in zip(c["coords"], c["values"]):
+                t.set(feo.Coordinate(co), v)
+            for co, v in zip(c["coords"], c["values"]):
+                assert t.get(feo.Coordinate(co)) == v
+        elif op == "get_err":
+            t = feo.Tensor(feo.Shape(c["shape"]), c["data"])
+            for co in c["coords"]:
+                with pytest.raises(feo.ShapeError):
+                    t.get(feo.Coordinate(co))
+        elif op == "set_err":
+            t = feo.Tensor(feo.Shape(c["shape"]), c["data"])
+            for co, v in zip(c["coords"], c["values"]):
+                with pytest.raises(feo.ShapeError):
+                    t.set(feo.Coordinate(co), v)
+        elif op == "from_tensor_err":
+            t = feo.Tensor(feo.Shape(c["shape"]), c["data"])
+            with pytest.raises(feo.ShapeError):
+                (feo.Matrix if c["kind"] == "matrix" else feo.Vector).from_tensor(t)
+    # matrix.rs:324-371 / vector.rs:304-331: Index / IndexMut / set through Deref
+    m = feo.Matrix(feo.shape(2, 2), [1.0, 2.0, 3.0, 4.0])
+    m[feo.coord(1, 0)] = 5.0
+    assert [m[feo.coord(i, j)] for i in range(2) for j in range(2)] == [1.0, 2.0, 5.0, 4.0]
+    v = feo.Vector([1.0, 2.0, 3.0, 4.0])
+    v[2] = 5.0
+    assert v[2] == 5.0 and v.size() == 4
+
+
+def test_panic_preconditions(feo):
+    a = feo.Tensor(feo.shape(2, 3), np.zeros(6, np.float32))
+    b = feo.Tensor(feo.shape(3, 2), np.zeros(6, np.float32))
+    with pytest.raises(feo.ReferencePanic):  # tensor.rs:366
+        a + b
+    for bad in ([1, 0], [0, 0], [2], [0, 1, 1]):
+        with pytest.raises(feo.ReferencePanic):
+            a.sum(bad)
+    with pytest.raises(feo.ReferencePanic):  # matrix.rs:78
+        feo.Matrix.from_tensor(a).matmul(feo.Matrix.from_tensor(a))
+    with pytest.raises(feo.ReferencePanic):  # vector.rs:72
+        feo.Vector([1.0, 2.0]).vecmul(feo.Vector([1.0, 2.0, 3.0]))
+    with pytest.raises(feo.ReferencePanic):  # matrix.rs:93
+        feo.Matrix.from_tensor(a).vecmul(feo.Vector([1.0, 2.0]))
+
+
+# ---- elementwise: bit-exact on random data, every dtype, ragged sizes ---------------------------------------
+@pytest.mark.parametrize("dt", ALL)
+def test_elementwise_bit_exact(feo, oracle, dt):
+    rng = np.random.default_rng(100)
+    for n in (1, 3, 255, 1024, 4097, (1 << 20) + 3):
+        a = rand(oracle, rng, dt, n)
+        b = rand(oracle, rng, dt, n, 1.0, 2.0) if dt in FLOATS else (np.abs(rand(oracle, rng, dt, n)) + 1).astype(a.dtype)
+        ta, tb = feo.Tensor(feo.shape(n), a), feo.Tensor(feo.shape(n), b)
+        for op in ("add", "sub", "mul", "div"):
+            got = {"add": ta + tb, "sub": ta - tb, "mul": ta * tb, "div": ta / tb}[op].to_numpy()
+            np.testing.assert_array_equal(got, oracle.ewise(op, a, b), err_msg=f"{dt} {op} n={n}")
+            s = b[0]
+            got = {"add": ta + s, "sub": ta - s, "mul": ta * s, "div": ta / s}[op].to_numpy()
+            np.testing.assert_array_equal(got, oracle.ewise_scalar(op, a, s), err_msg=f"{dt} scalar {op} n={n}")
+
+
+def test_elementwise_special_values_and_wrap(feo, oracle):
+    a = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, 1e-45, 3.4e38, 1.17549435e-38], np.float32)
+    b = np.array([0.0, 0.0, 0.0, np.inf, 1.0, 2.0, 2.0, 3.4e38, 3.0], np.float32)
+    ta, tb = feo.Tensor(feo.shape(a.size), a), feo.Tensor(feo.shape(b.size), b)
+    for op, r in (("add", ta + tb), ("sub", ta - tb), ("mul", ta * tb), ("div", ta / tb)):
+        got, want = r.to_numpy(), oracle.ewise(op, a, b)
+        np.testing.assert_array_equal(got.view(np.uint32)[~np.isnan(want)], want.view(np.uint32)[~np.isnan(want)], err_msg=op)
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+    ia = np.array([2 ** 31 - 1, -2 ** 31, 7, -7], np.int32)
+    ib = np.array([1, -1, 2, 2], np.int32)
+    ti, tj = feo.Tensor(feo.shape(4), ia), feo.Tensor(feo.shape(4), ib)
+    np.testing.assert_array_equal((ti + tj).to_numpy(), oracle.ewise("add", ia, ib))
+    np.testing.assert_array_equal((ti * tj).to_numpy(), oracle.ewise("mul", ia, ib))
+    np.testing.assert_array_equal((ti / np.int32(2)).to_numpy(), oracle.ewise_scalar("div", ia, 2))  # truncation toward zero
+    # x/0 and MIN/-1: the reference panics; the kernel writes 0 and raises the sticky flag
+    ctx = feo.Context.default()
+    assert ctx.arith_flag() == 0
+    r = (ti / feo.Tensor(feo.shape(4), np.array([1, -1, 0, 1], np.int32))).to_numpy()
+    assert ctx.arith_flag() == 1 and ctx.arith_flag() == 0
+    np.testing.assert_array_equal(r, np.array([2 ** 31 - 1, 0, 0, -7], np.int32))
+
+
+def test_elementwise_unaligned_pointers(feo, oracle):
+    """Raw C-ABI call on pointers offset by one element: exercises the scalar path."""
+    import feotensor_b200._lib as L
+    ctx = feo.Context.default()
+    rng = np.random.default_rng(7)
+    n = 10001
+    a, b = rand(oracle, rng, "f32", n + 1), rand(oracle, rng, "f32", n + 1)
+    ta, tb, to = feo.Tensor(feo.shape(n + 1), a), feo.Tensor(feo.shape(n + 1), b), feo.Tensor.zeros(feo.shape(n + 1), "f32")
+    ctx.check(ctx.lib.feo_ewise(ctx.handle, L.MUL, L.F32, C.c_void_p(to.data.ptr + 4), C.c_void_p(ta.data.ptr + 4),
+                                C.c_void_p(tb.data.ptr + 4), n))
+    np.testing.assert_array_equal(to.to_numpy()[1:], oracle.ewise("mul", a[1:], b[1:]))
+    assert to.to_numpy()[0] == 0
+
+
+BCAST_CASES = [
+    ((8, 1, 64), (1, 12, 64)),          # config-2 pattern: both operands invariant somewhere (8x4 tiles)
+    ((3, 1, 64), (1, 5, 64)),           # fewer than 8 rows: 4x4 tiles with ragged edges
+    ((16, 1, 4096), (1, 9, 4096)),      # full-width inner rows
+    ((37, 1), (1, 128)),                # outer-product pattern (a splat along the inner axis)
+    ((1, 130), (33, 1)),                # mirrored outer product
+    ((33, 64), (1, 64)),                # matrix + row bias: only b invariant
+    ((1, 64), (33, 64)),                # only a invariant
+    ((5, 7, 12), (5, 7, 12)),           # same shape -> collapses to the flat kernel
+    ((5, 1, 7, 1, 8), (1, 3, 7, 2, 8)), # rank 5, several broadcast dims
+    ((4, 1, 6), (1, 5, 6)),             # inner not a multiple of 4 (f32): scalar fallback
+    ((7, 1, 1), (1, 1, 9)),             # extent-1 dims dropped
+    ((2, 3, 1, 16), (2, 1, 5, 16)),
+    ((1,), (1,)),
+    ((6, 1, 32), (6, 4, 1)),            # b splat along the inner axis, a invariant along dim 1
+]
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64", "i32", "i64"])
+def test_broadcast_bit_exact(feo, oracle, dt):
+    rng = np.random.default_rng(200)
+    for sa, sb in BCAST_CASES:
+        a = rand(oracle, rng, dt, sa)
+        b = rand(oracle, rng, dt, sb, 1.0, 2.0) if dt in FLOATS else (np.abs(rand(oracle, rng, dt, sb)) + 1).astype(a.dtype)
+        ta, tb = feo.Tensor(feo.Shape(sa), a), feo.Tensor(feo.Shape(sb), b)
+        for op in ("mul", "add", "sub", "div"):
+            got = ta.broadcast(op, tb)
+            want = oracle.ewise_broadcast(op, a, b)
+            assert tuple(got.shape().dims) == want.shape
+            np.testing.assert_array_equal(got.to_numpy(), want, err_msg=f"{dt} {op} {sa} {sb}")
+    with pytest.raises(feo.ShapeError):
+        feo.Tensor(feo.shape(2, 3), np.zeros(6, np.float32)).broadcast("mul", feo.Tensor(feo.shape(4, 3), np.zeros(12, np.float32)))
+
+
+def test_broadcast_tile_variants_agree(feo, oracle):
+    """Every tiling of the broadcast kernel (knob 0) produces the same bits."""
+    import feotensor_b200._lib as L
+    ctx = feo.Context.default()
+    rng = np.random.default_rng(201)
+    a, b = rand(oracle, rng, "f32", (19, 1, 256)), rand(oracle, rng, "f32", (1, 23, 256))
+    ta, tb = feo.Tensor(feo.shape(19, 1, 256), a), feo.Tensor(feo.shape(1, 23, 256), b)
+    want = oracle.ewise_broadcast("mul", a, b)
+    try:
+        for knob in (0, 1, 2, 3, 4):
+            ctx.tune(L.KNOB_BCAST_TILE, knob)
+            np.testing.assert_array_equal(ta.broadcast("mul", tb).to_numpy(), want, err_msg=f"knob {knob}")
+    finally:
+        ctx.tune(L.KNOB_BCAST_TILE, 0)
+
+
+# ---- reductions ---------------------------------------------------------------------------------------------------
+REDUCE_CASES = [
+    # (shape, axes)                                  kernel it lands on
+    ((64, 128, 256), [0, 2]),                        # BASELINE config 1: [R,K,R] rows geometry
+    ((64, 128, 256), [0]),                           # cols
+    ((64, 128, 256), [2]),                           # rows, warp per output
+    ((64, 128, 256), [1]),                           # [K,R,K] cols with k1 > 1
+    ((64, 128, 256), [0, 1]), ((64, 128, 256), [1, 2]), ((64, 128, 256), [0, 1, 2]), ((64, 128, 256), []),
+    ((300, 200, 8), [0]), ((300, 200, 8), [2]), ((300, 200, 8), [0, 2]), ((300, 200, 8), [1, 2]),  # config-3 pattern (micro r2=8)
+    ((1000, 16), [1]), ((1000, 4), [1]), ((1000, 2), [1]), ((77, 32), [1]), ((50, 3, 2), [0, 2]),   # micro widths
+    ((1000, 3), [1]), ((1000, 5), [1]), ((129, 7, 6), [0, 2]),                                     # micro, run-time r2
+    ((5, 1000), [1]), ((5, 1001), [1]), ((3, 40000), [1]), ((1, 100003), [1]),                     # rows, ragged, split columns
+    ((100003,), [0]), ((1 << 21,), []),                                                            # full reductions, split
+    ((4097, 33), [0]), ((20000, 4), [0]), ((7, 9), [0]), ((1, 9), [0]), ((9, 1), [0]),             # cols: ragged / tiny
+    ((3, 4, 5, 6, 7), [0, 2, 4]), ((3, 4, 5, 6, 7), [1, 3]), ((2, 3, 4, 5, 6, 7), [0, 2, 4]),      # >4 groups: generic
+    ((6, 5, 4, 3), [1, 3]), ((6, 5, 4, 3), [0, 2]), ((6, 5, 4, 3), [1, 2]),
+    ((1,), [0]), ((1, 1, 1), [1]), ((2, 1, 3), [1]),
+]
+
+
+def _terms(x, axes):
+    ax = tuple(axes) if axes else None
+    return np.atleast_1d(np.abs(x.astype(np.float64)).sum(axis=ax)), int(np.prod([x.shape[a] for a in axes]) if axes else x.size)
+
+
+@pytest.mark.parametrize("dt", ALL)
+def test_reductions_vs_oracle(feo, oracle, dt):
+    rng = np.random.default_rng(300)
+    for shape, axes in REDUCE_CASES:
+        x = rand(oracle, rng, dt, shape)
+        t = feo.Tensor(feo.Shape(shape), x)
+        for kind in ("sum", "mean", "var", "max", "min"):
+            got = getattr(t, kind)(axes)
+            want = oracle.reduce(kind, x, axes)
+            assert tuple(got.shape().dims) == want.shape, (shape, axes, kind)
+            g = got.to_numpy()
+            msg = f"{dt} {kind} {shape} {axes}"
+            if dt in INTS or kind in ("max", "min"):
+                np.testing.assert_array_equal(g, want, err_msg=msg)
+                continue
+            abs_sum, n = _terms(x, axes)
+            nd = float(oracle.reduce_divisor(dt, shape, axes))
+            if kind == "sum":
+                assert_sum_like(g.reshape(-1), want.reshape(-1), abs_sum.reshape(-1), n, dt, msg)
+            elif kind == "mean":
+                assert_sum_like(g.reshape(-1), want.reshape(-1), abs_sum.reshape(-1) / nd * (1 + 4 * U[dt]), n + 1, dt, msg)
+            else:
+                # var: compare with the exact (f64 / extended) value; both the two-pass reference and the
+                # one-pass Welford result are within a few gamma_n of sum (x-mu)^2 / n
+                xx = x.astype(np.longdouble)
+                ax = tuple(axes) if axes else None
+                exact = np.atleast_1d(xx.var(axis=ax)).astype(np.float64).reshape(-1)
+                scale = np.atleast_1d((xx * xx).sum(axis=ax)).astype(np.float64).reshape(-1) / nd
+                bound = 8 * gamma(n + 2, dt) * scale + 1e-300
+                assert np.all(np.abs(g.reshape(-1).astype(np.float64) - exact) <= bound), msg
+                assert np.all(np.abs(want.reshape(-1).astype(np.float64) - exact) <= bound), msg + " (oracle)"
+
+
+def test_reduction_split_counts_agree(feo, oracle):
+    """Forcing the split count exercises stage 2; integers must stay bit-exact for every split."""
+    import feotensor_b200._lib as L
+    ctx = feo.Context.default()
+    rng = np.random.default_rng(301)
+    cases = [((513, 260), [0]), ((300, 64, 8), [0, 2]), ((9, 70000), [1]), ((200000,), [0])]
+    try:
+        for shape, axes in cases:
+            x = rand(oracle, rng, "i64", shape)
+            xf = rand(oracle, rng, "f32", shape)
+            t, tf = feo.Tensor(feo.Shape(shape), x), feo.Tensor(feo.Shape(shape), xf)
+            for S in (0, 1, 2, 3, 7, 16):
+                ctx.tune(L.KNOB_REDUCE_SPLIT, S)
+                for kind in ("sum", "var", "max", "min", "mean"):
+                    np.testing.assert_array_equal(getattr(t, kind)(axes).to_numpy(), oracle.reduce(kind, x, axes), err_msg=f"S={S} {kind} {shape}")
+                np.testing.assert_array_equal(tf.max(axes).to_numpy(), oracle.reduce("max", xf, axes))
+                abs_sum, n = _terms(xf, axes)
+                assert_sum_like(tf.sum(axes).to_numpy().reshape(-1), oracle.reduce("sum", xf, axes).reshape(-1), abs_sum, n, "f32")
+    finally:
+        ctx.tune(L.KNOB_REDUCE_SPLIT, 0)
+
+
+def test_mean_divisor_quirk_on_device(feo, oracle):
+    """Vector::mean() takes the axes=[] branch (vector.rs:51): n counts the whole size in T and saturates at
+    2^24 for f32 (tensor.rs:125-129).  All-ones data makes the sum exact, so the quirk is visible bit for bit."""
+    n = (1 << 24) + 64
+    v = feo.Tensor.fill(feo.shape(n), 0.5, "f32")
+    # every partial sum is a multiple of 0.5 below 2^24, hence exact in any order: sum = n/2; divisor = 2^24, not n
+    assert v.sum([]).to_numpy()[0] == np.float32(n // 2)
+    assert v.mean([]).to_numpy()[0] == np.float32(n // 2) / np.float32(1 << 24)
+    assert v.mean([0]).to_numpy()[0] == np.float32(n // 2) / np.float32(1 << 24)
+    assert v.mean([]).to_numpy()[0] != np.float32(0.5)
+    assert oracle.reduce_divisor("f32", (n,), []) == np.float32(1 << 24)
+
+
+def test_partial_reductions_and_var_merge(feo, oracle):
+    """The building blocks of the sharded path: per-shard partials combined by feo_var_merge equal the
+    single-device result within the float bound (bit-exact for the integer two-pass scheme)."""
+    import feotensor_b200._lib as L
+    ctx = feo.Context.default()
+    lib = ctx.lib
+    rng = np.random.default_rng(302)
+    G, rows, K = 4, 64, 96
+    x = rand(oracle, rng, "f32", (G * rows, K))
+    shards = [feo.Tensor(feo.shape(rows, K), x[g * rows:(g + 1) * rows]) for g in range(G)]
+    partials = feo.Tensor.zeros(feo.shape(G, 2, K), "f32")
+    for g, s in enumerate(shards):
+        ctx.check(lib.feo_reduce_partial(ctx.handle, L.VAR, L.F32, C.c_void_p(partials.data.ptr + g * 2 * K * 4),
+                                         C.c_void_p(s.data.ptr), 2, L.sizes([rows, K]), 1, L.sizes([0])))
+    out = feo.Tensor.zeros(feo.shape(K), "f32")
+    div = np.array([oracle.reduce_divisor("f32", (G * rows, K), [0])], np.float32)
+    ctx.check(lib.feo_var_merge(ctx.handle, L.F32, C.c_void_p(out.data.ptr), C.c_void_p(partials.data.ptr), G, K, rows,
+                                div.ctypes.data_as(C.c_void_p)))
+    exact = x.astype(np.float64).var(axis=0)
+    np.testing.assert_allclose(out.to_numpy(), exact, rtol=2e-5)
+    np.testing.assert_allclose(out.to_numpy(), feo.Tensor(feo.shape(G * rows, K), x).var([0]).to_numpy(), rtol=2e-5)
+    # integer two-pass across shards: sum partials -> truncated mean -> squared deviations -> divide
+    xi = rand(oracle, rng, "i32", (G * rows, K))
+    ishards = [feo.Tensor(feo.shape(rows, K), xi[g * rows:(g + 1) * rows]) for g in range(G)]
+    total = None
+    for s in ishards:
+        p = feo.Tensor.zeros(feo.shape(K), "i32")
+        ctx.check(lib.feo_reduce_partial(ctx.handle, L.SUM, L.I32, C.c_void_p(p.data.ptr), C.c_void_p(s.data.ptr), 2,
+                                         L.sizes([rows, K]), 1, L.sizes([0])))
+        total = p if total is None else total + p
+    n = np.int32(oracle.reduce_divisor("i32", (G * rows, K), [0]))
+    mean = total / n
+    sq = None
+    for s in ishards:
+        p = feo.Tensor.zeros(feo.shape(K), "i32")
+        ctx.check(lib.feo_reduce_sqdev(ctx.handle, L.I32, C.c_void_p(p.data.ptr), C.c_void_p(s.data.ptr), C.c_void_p(mean.data.ptr),
+                                       2, L.sizes([rows, K]), 1, L.sizes([0])))
+        sq = p if sq is None else sq + p
+    np.testing.assert_array_equal((sq / n).to_numpy(), oracle.reduce("var", xi, [0]))
+
+
+# ---- products ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", ALL)
+def test_outer_product_bit_exact(feo, oracle, dt):
+    rng = np.random.default_rng(400)
+    for na, nb in ((1, 1), (3, 5), (64, 64), (129, 1000), (1000, 129), (33, 4096)):
+        a, b = rand(oracle, rng, dt, na), rand(oracle, rng, dt, nb)
+        r = feo.Vector(a).prod(feo.Vector(b))
+        assert r.shape().dims == [na, nb]
+        np.testing.assert_array_equal(r.to_numpy(), oracle.prod(a, b), err_msg=f"{dt} {na}x{nb}")
+    a, b = rand(oracle, rng, dt, (3, 4)), rand(oracle, rng, dt, (2, 8))
+    r = feo.Tensor(feo.shape(3, 4), a).prod(feo.Tensor(feo.shape(2, 8), b))
+    assert r.shape().dims == [3, 4, 2, 8]
+    np.testing.assert_array_equal(r.to_numpy(), oracle.prod(a, b))
+
+
+@pytest.mark.parametrize("dt", ALL)
+def test_dot_matvec_vecmat(feo, oracle, dt):
+    rng = np.random.default_rng(500)
+    for n in (1, 2, 31, 1000, 4099, 1 << 18):
+        a, b = rand(oracle, rng, dt, n), rand(oracle, rng, dt, n)
+        got = feo.Vector(a).vecmul(feo.Vector(b))
+        want = oracle.dot(a, b)
+        assert got.shape().dims == [1]
+        if dt in INTS:
+            np.testing.assert_array_equal(got.to_numpy(), want)
+        else:
+            assert_sum_like(got.to_numpy(), want, np.abs(a.astype(np.float64) * b).sum(), n + 1, dt, f"dot n={n}")
+    for m, k in ((1, 1), (7, 5), (33, 1000), (500, 36), (64, 4096)):
+        A, v, w = rand(oracle, rng, dt, (m, k)), rand(oracle, rng, dt, k), rand(oracle, rng, dt, m)
+        tA = feo.Matrix(feo.shape(m, k), A)
+        g1, w1 = tA.vecmul(feo.Vector(v)).to_numpy(), oracle.matvec(A, v)
+        g2, w2 = feo.Vector(w).matmul(tA).to_numpy(), oracle.vecmat(w, A)
+        B2 = rand(oracle, rng, dt, (m, k))
+        g3, w3 = feo.dot_batched(tA, feo.Matrix(feo.shape(m, k), B2)).to_numpy(), oracle.dot_batched(A, B2)
+        if dt in INTS:
+            np.testing.assert_array_equal(g1, w1); np.testing.assert_array_equal(g2, w2); np.testing.assert_array_equal(g3, w3)
+        else:
+            assert_sum_like(g1, w1, (np.abs(A.astype(np.float64)) * np.abs(v)).sum(axis=1), k + 1, dt, f"matvec {m}x{k}")
+            assert_sum_like(g2, w2, (np.abs(A.astype(np.float64)) * np.abs(w)[:, None]).sum(axis=0), m + 1, dt, f"vecmat {m}x{k}")
+            assert_sum_like(g3, w3, (np.abs(A.astype(np.float64)) * np.abs(B2)).sum(axis=1), k + 1, dt, f"bdot {m}x{k}")
+
+
+@pytest.mark.parametrize("dt", ALL)
+def test_matmul_simt_vs_oracle(feo, oracle, dt):
+    rng = np.random.default_rng(600)
+    for m, k, n in ((1, 1, 1), (2, 3, 4), (17, 33, 9), (128, 128, 128), (256, 64, 384), (130, 70, 257), (64, 1000, 48)):
+        A, B = rand(oracle, rng, dt, (m, k)), rand(oracle, rng, dt, (k, n))
+        got = feo.Matrix(feo.shape(m, k), A).matmul(feo.Matrix(feo.shape(k, n), B), algo="simt")
+        want = oracle.matmul(A, B)
+        assert got.shape().dims == [m, n]
+        if dt in INTS:
+            np.testing.assert_array_equal(got.to_numpy(), want, err_msg=f"{dt} {m}x{k}x{n}")
+        else:
+            terms = np.abs(A.astype(np.float64)) @ np.abs(B.astype(np.float64))
+            assert_sum_like(got.to_numpy(), want, terms, k + 1, dt, f"matmul {m}x{k}x{n}")
+
+
+def test_device_generator_matches_host_twin(feo, oracle):
+    for dt, lo, hi in (("f32", -1.0, 1.0), ("f32", 1.0, 2.0), ("f64", -1.0, 1.0), ("i32", -1000, 1000), ("i64", -1000, 1000), ("u32", 0, 2000)):
+        t = feo.Tensor.uniform(feo.shape(1000, 37), seed=42, lo=lo, hi=hi, dtype=dt, first_index=12345)
+        want = oracle.fill_uniform(dt, 37000, 42, 12345, lo, hi)
+        np.testing.assert_array_equal(t.to_numpy().reshape(-1), want)
+        assert want.min() >= lo and want.max() < hi
+    # strided regeneration of single columns
+    np.testing.assert_array_equal(oracle.fill_uniform("f32", 10, 42, 5, -1, 1, stride=37),
+                                  oracle.fill_uniform("f32", 37 * 10, 42, 0, -1, 1)[5::37])
