@@ -255,7 +255,7 @@ def run_suite(torch, feo, L, ctx, hbm_peak, tf_peak):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-suite", action="store_true")
@@ -408,7 +408,7 @@ def main():
                    "l2": "32 GiB written per step per GPU >> 126 MB L2 (b, 64 MiB, is meant to stay L2-resident)",
                    "algorithmic_bytes_per_launch": SLAB_BYTES},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": traffic, "kernel": "bcast_tile_kernel<float,MUL,8,4>", "launch_ms": launch_ms, "peak_source": peak_src},
+                     "traffic": traffic, "kernel": "bcast_tile_kernel<float,MUL,16B,8,4>", "launch_ms": launch_ms, "peak_source": peak_src},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 4 * (ROWS_PER_RANK * D + D * D),
                 "d2h_bytes_per_step": 4 * ROWS_PER_RANK * D * D, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": int(launches), "clocks": clocks,

@@ -13,10 +13,11 @@
 
 // ---- context ------------------------------------------------------------------------------------
 enum feo_knob {
-    FEO_KNOB_BCAST_TILE = 0,    // 0 = auto, 1 = 8x4, 2 = 4x4, 3 = 1x1 (generic vector), 4 = scalar fallback
+    FEO_KNOB_BCAST_TILE = 0,    // 0 = auto, 2 = 4x4 tiles, 3 = 1x1 vector tiles, 4 = scalar fallback (see broadcast_vec)
     FEO_KNOB_REDUCE_SPLIT = 1,  // 0 = auto, else forced number of splits S
     FEO_KNOB_REDUCE_BLOCKS_PER_SM = 2,  // target resident blocks per SM used by the split planner (0 = auto)
     FEO_KNOB_MATMUL_TF32_STAGES = 3,
+    FEO_KNOB_BCAST_LCHUNK = 4,  // rows of the loop dimension per thread in the hold+stream broadcast kernel (0 = auto)
     FEO_KNOB_COUNT = 8
 };
 
@@ -102,11 +103,18 @@ template <int OP, typename T> __device__ __forceinline__ T apply_op(T a, T b, in
 template <typename T, int N> struct alignas(sizeof(T) * N) AVec { T v[N]; };
 template <typename T> struct VecN { static constexpr int value = 16 / sizeof(T); };
 
+// sm_100 adds 256-bit global accesses (LDG.E.256 / STG.E.256): one 32-byte sector per thread per instruction.
+template <typename T, int BYTES> struct VecW { static constexpr int value = BYTES / (int)sizeof(T); };
+
 // Streaming (read-once) load: bypass L1 allocation.
 template <typename V> __device__ __forceinline__ V ld_stream(const V *p) {
-    static_assert(sizeof(V) == 16 || sizeof(V) == 8 || sizeof(V) == 4, "vector size");
+    static_assert(sizeof(V) == 32 || sizeof(V) == 16 || sizeof(V) == 8 || sizeof(V) == 4, "vector size");
     V r;
-    if constexpr (sizeof(V) == 16) {
+    if constexpr (sizeof(V) == 32) {
+        unsigned long long t[4];
+        asm("ld.global.nc.L1::no_allocate.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(t[0]), "=l"(t[1]), "=l"(t[2]), "=l"(t[3]) : "l"(p));
+        __builtin_memcpy(&r, t, 32);
+    } else if constexpr (sizeof(V) == 16) {
         uint4 t;
         asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
         __builtin_memcpy(&r, &t, 16);
@@ -124,7 +132,11 @@ template <typename V> __device__ __forceinline__ V ld_stream(const V *p) {
 // Reused (keep in L1/L2) read-only load.
 template <typename V> __device__ __forceinline__ V ld_keep(const V *p) {
     V r;
-    if constexpr (sizeof(V) == 16) {
+    if constexpr (sizeof(V) == 32) {
+        unsigned long long t[4];
+        asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(t[0]), "=l"(t[1]), "=l"(t[2]), "=l"(t[3]) : "l"(p));
+        __builtin_memcpy(&r, t, 32);
+    } else if constexpr (sizeof(V) == 16) {
         uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
         __builtin_memcpy(&r, &t, 16);
     } else if constexpr (sizeof(V) == 8) {
@@ -138,7 +150,10 @@ template <typename V> __device__ __forceinline__ V ld_keep(const V *p) {
 }
 // Streaming store (evict-first): results are written once and not re-read by the kernel.
 template <typename V> __device__ __forceinline__ void st_stream(V *p, const V &v) {
-    if constexpr (sizeof(V) == 16) {
+    if constexpr (sizeof(V) == 32) {
+        unsigned long long t[4]; __builtin_memcpy(t, &v, 32);
+        asm volatile("st.global.cs.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(t[0]), "l"(t[1]), "l"(t[2]), "l"(t[3]) : "memory");
+    } else if constexpr (sizeof(V) == 16) {
         uint4 t; __builtin_memcpy(&t, &v, 16);
         asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w) : "memory");
     } else if constexpr (sizeof(V) == 8) {
@@ -151,6 +166,7 @@ template <typename V> __device__ __forceinline__ void st_stream(V *p, const V &v
 }
 
 static inline bool feo_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool feo_aligned32(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 static inline size_t feo_ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
 
 // ---- entry points implemented per kernel family (called from feo_api.cu) ---------------------------

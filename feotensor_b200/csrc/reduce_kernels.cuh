@@ -96,7 +96,8 @@ template <typename T> struct Acc<T, K_WELFORD> {
         T q = (T)0;
 #pragma unroll
         for (int i = 0; i < N; ++i) { const T c = x[i] - bm; q += c * c; }
-        merge_raw((T)N, bm, q);
+        if (n == (T)0) { n = (T)N; mean = bm; m2 = q; }  // first batch: nothing to merge, no division
+        else merge_raw((T)N, bm, q);
     }
 };
 
@@ -151,6 +152,7 @@ struct Geom {
     long long xblocks;         // blocks along the thread-mapped axis
     int fin;
     int lanes;                 // rows kernel: 32 (warp per output) or 256 (block per output)
+    int lx;                    // rows kernel: lanes along the row (power of two <= lanes); lanes / lx rows at a time
 };
 
 // ---- cols: in[k1][r1][k2] -> out[k1][k2], threads along k2 ---------------------------------------------
@@ -210,65 +212,123 @@ __global__ void __launch_bounds__(kThreads) reduce_cols_kernel(T *__restrict__ o
     for (int k = 0; k < W; ++k) emit(acc[k], out, partial, o0 + k, s, G.nout, G.S, G.fin, divisor, flag);
 }
 
-// ---- micro: in[k1][r1][k2][r2] with 2 <= r2 <= 32, one thread per output ---------------------------------
-// R2C > 0: compile-time r2 (vector loads); R2C == 0: run-time r2, scalar loads.
-template <typename T, int KIND, int R2C>
+// ---- micro: in[k1][r1][k2][r2] with 2 <= r2 <= 32 ----------------------------------------------------------
+// R2C > 0: compile-time r2.  A thread owns OUTS outputs (k2, k2 + 256, ...) and reads each one's r2 contiguous
+// elements with 256-bit loads (one full 32-byte sector per access), OUTS x U of them in flight per step.
+// R2C == 0: run-time r2, one output per thread, scalar loads.
+// WIDE (r1 == 1: a single row per output): no row loop to unroll, so more outputs per thread keep ~256 B in flight.
+template <int R2C, bool WIDE> struct MicroShape {
+    static constexpr int OUTS = (R2C == 0) ? 1 : (WIDE ? ((32 / R2C) > 8 ? 8 : ((32 / R2C) < 2 ? 2 : (32 / R2C))) : (R2C <= 16 ? 4 : 2));
+    static constexpr int U = (R2C == 0 || WIDE) ? 1 : ((64 / (OUTS * R2C)) > 8 ? 8 : ((64 / (OUTS * R2C)) < 1 ? 1 : (64 / (OUTS * R2C))));
+};
+template <typename T, int KIND, int R2C, bool WIDE>
 __global__ void __launch_bounds__(kThreads) reduce_micro_kernel(T *__restrict__ out, void *__restrict__ partial,
                                                                 const T *__restrict__ in, const T *__restrict__ aux,
                                                                 const __grid_constant__ Geom G, T divisor, int *flag) {
+    constexpr int OUTS = MicroShape<R2C, WIDE>::OUTS;
     long long blk = blockIdx.x;
     const long long bx = blk % G.xblocks; blk /= G.xblocks;
     const long long s = blk % G.S;
     const long long k1 = blk / G.S;
-    const long long k2 = bx * kThreads + threadIdx.x;
-    if (k2 >= G.K2) return;
+    const long long k2_0 = bx * (kThreads * OUTS) + threadIdx.x;
+    if (k2_0 >= G.K2) return;
     const long long r_lo = s * G.c1;
     const long long r_hi = (r_lo + G.c1 < G.R1) ? r_lo + G.c1 : G.R1;
-    const long long o = k1 * G.K2 + k2;
     const long long rstride = G.K2 * G.R2;
-    const T *base = in + ((k1 * G.R1) * G.K2 + k2) * G.R2;
-    Acc<T, KIND> acc;
-    acc.init(aux_val<KIND>(aux, o));
+    const T *base = in + ((k1 * G.R1) * G.K2 + k2_0) * G.R2;
+    Acc<T, KIND> acc[OUTS];
+    bool live[OUTS];
+#pragma unroll
+    for (int j = 0; j < OUTS; ++j) {
+        live[j] = (k2_0 + (long long)j * kThreads) < G.K2;
+        acc[j].init(live[j] ? aux_val<KIND>(aux, k1 * G.K2 + k2_0 + (long long)j * kThreads) : (T)0);
+    }
     if constexpr (R2C > 0) {
-        constexpr int VN = VecN<T>::value;
+        constexpr int VN = VecW<T, 32>::value;  // 256-bit loads: every access is exactly one 32-byte sector or more
         constexpr int W = R2C < VN ? R2C : VN;
         constexpr int NV = R2C / W;
-        constexpr int U = (32 / R2C) > 0 ? ((32 / R2C) > 8 ? 8 : (32 / R2C)) : 1;
+        constexpr int U = MicroShape<R2C, WIDE>::U;
         using V = AVec<T, W>;
         long long r = r_lo;
+        if constexpr (WIDE) {  // r1 == 1: one row per output, straight-line code (the accumulator folds to one batch)
+            V v[OUTS][NV];
+#pragma unroll
+            for (int j = 0; j < OUTS; ++j)
+                if (live[j]) {
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) v[j][i] = ld_stream(reinterpret_cast<const V *>(base + (long long)j * kThreads * G.R2) + i);
+                }
+#pragma unroll
+            for (int j = 0; j < OUTS; ++j)
+                if (live[j]) {
+                    T x[R2C];
+#pragma unroll
+                    for (int i = 0; i < NV; ++i)
+#pragma unroll
+                        for (int k = 0; k < W; ++k) x[i * W + k] = v[j][i].v[k];
+                    Acc<T, KIND> a1;
+                    a1.init(aux_val<KIND>(aux, k1 * G.K2 + k2_0 + (long long)j * kThreads));
+                    a1.push_batch(x);
+                    emit(a1, out, partial, k1 * G.K2 + k2_0 + (long long)j * kThreads, s, G.nout, G.S, G.fin, divisor, flag);
+                }
+            return;
+        } else {
         for (; r + U <= r_hi; r += U) {
-            V v[U][NV];
+            V v[OUTS][U][NV];
 #pragma unroll
-            for (int u = 0; u < U; ++u)
+            for (int j = 0; j < OUTS; ++j)
+                if (live[j]) {
 #pragma unroll
-                for (int j = 0; j < NV; ++j) v[u][j] = ld_stream(reinterpret_cast<const V *>(base + (r + u) * rstride) + j);
+                    for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                T x[R2C];
+                        for (int i = 0; i < NV; ++i)
+                            v[j][u][i] = ld_stream(reinterpret_cast<const V *>(base + (long long)j * kThreads * G.R2 + (r + u) * rstride) + i);
+                }
 #pragma unroll
-                for (int j = 0; j < NV; ++j)
+            for (int j = 0; j < OUTS; ++j)
+                if (live[j]) {
 #pragma unroll
-                    for (int k = 0; k < W; ++k) x[j * W + k] = v[u][j].v[k];
-                acc.push_batch(x);
-            }
+                    for (int u = 0; u < U; ++u) {
+                        T x[R2C];
+#pragma unroll
+                        for (int i = 0; i < NV; ++i)
+#pragma unroll
+                            for (int k = 0; k < W; ++k) x[i * W + k] = v[j][u][i].v[k];
+                        acc[j].push_batch(x);
+                    }
+                }
         }
         for (; r < r_hi; ++r) {
-            T x[R2C];
+            V v[OUTS][NV];
 #pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                const V v = ld_stream(reinterpret_cast<const V *>(base + r * rstride) + j);
+            for (int j = 0; j < OUTS; ++j)
+                if (live[j]) {
 #pragma unroll
-                for (int k = 0; k < W; ++k) x[j * W + k] = v.v[k];
-            }
-            acc.push_batch(x);
+                    for (int i = 0; i < NV; ++i) v[j][i] = ld_stream(reinterpret_cast<const V *>(base + (long long)j * kThreads * G.R2 + r * rstride) + i);
+                }
+#pragma unroll
+            for (int j = 0; j < OUTS; ++j)
+                if (live[j]) {
+                    T x[R2C];
+#pragma unroll
+                    for (int i = 0; i < NV; ++i)
+#pragma unroll
+                        for (int k = 0; k < W; ++k) x[i * W + k] = v[j][i].v[k];
+                    acc[j].push_batch(x);
+                }
+        }
         }
     } else {
         for (long long r = r_lo; r < r_hi; ++r) {
             const T *p = base + r * rstride;
-            for (long long j = 0; j < G.R2; ++j) acc.push(__ldg(p + j));
+            for (long long j = 0; j < G.R2; ++j) acc[0].push(__ldg(p + j));
         }
     }
-    emit(acc, out, partial, o, s, G.nout, G.S, G.fin, divisor, flag);
+    if constexpr (!(R2C > 0 && WIDE)) {  // the WIDE path has emitted and returned above
+#pragma unroll
+        for (int j = 0; j < OUTS; ++j)
+            if (live[j]) emit(acc[j], out, partial, k1 * G.K2 + k2_0 + (long long)j * kThreads, s, G.nout, G.S, G.fin, divisor, flag);
+    }
 }
 
 // ---- rows: in[k1][r1][k2][r2], long r2; `lanes` threads cooperate on one output ----------------------------
@@ -299,21 +359,24 @@ __global__ void __launch_bounds__(kThreads) reduce_rows_kernel(T *__restrict__ o
         const long long rstride = G.K2 * G.R2;
         const long long obase = ((k1 * G.R1) * G.K2 + k2) * G.R2;
         acc.init(aux_val<KIND>(aux, o));
-        for (long long r = r_lo; r < r_hi; ++r) {
+        // lanes form an lx x ly grid: lx lanes stride the row, ly rows are walked concurrently (short rows
+        // would otherwise leave most of the lanes idle)
+        const int lx = G.lx, lxi = lane % lx, lyi = lane / lx, ly = lanes / lx;
+        for (long long r = r_lo + lyi; r < r_hi; r += ly) {
             const T *row = in + obase + r * rstride;
             const T *row2 = nullptr;
             if constexpr (LOADER == LD_MUL) row2 = in2 + obase + r * rstride;
             if constexpr (LOADER == LD_MATVEC) row2 = in2;
-            long long cv = c_lo + lane;
-            for (; cv + (long long)(U - 1) * lanes < c_hi; cv += (long long)U * lanes) {
+            long long cv = c_lo + lxi;
+            for (; cv + (long long)(U - 1) * lx < c_hi; cv += (long long)U * lx) {
                 V v[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) v[u] = ld_stream(reinterpret_cast<const V *>(row) + cv + (long long)u * lanes);
+                for (int u = 0; u < U; ++u) v[u] = ld_stream(reinterpret_cast<const V *>(row) + cv + (long long)u * lx);
                 if constexpr (LOADER == LD_MUL || LOADER == LD_MATVEC) {
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const V w = (LOADER == LD_MUL) ? ld_stream(reinterpret_cast<const V *>(row2) + cv + (long long)u * lanes)
-                                                       : ld_keep(reinterpret_cast<const V *>(row2) + cv + (long long)u * lanes);
+                        const V w = (LOADER == LD_MUL) ? ld_stream(reinterpret_cast<const V *>(row2) + cv + (long long)u * lx)
+                                                       : ld_keep(reinterpret_cast<const V *>(row2) + cv + (long long)u * lx);
 #pragma unroll
                         for (int k = 0; k < W; ++k) v[u].v[k] = w_mul(v[u].v[k], w.v[k]);
                     }
@@ -325,7 +388,7 @@ __global__ void __launch_bounds__(kThreads) reduce_rows_kernel(T *__restrict__ o
                     for (int k = 0; k < W; ++k) x[u * W + k] = v[u].v[k];
                 acc.push_batch(x);
             }
-            for (; cv < c_hi; cv += lanes) {
+            for (; cv < c_hi; cv += lx) {
                 V v = ld_stream(reinterpret_cast<const V *>(row) + cv);
                 if constexpr (LOADER == LD_MUL || LOADER == LD_MATVEC) {
                     const V w = ld_keep(reinterpret_cast<const V *>(row2) + cv);
@@ -458,6 +521,7 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
     G.fin = fin;
     G.S = G.S1 = G.S2 = 1;
     G.lanes = 32;
+    G.lx = 32;
     const long long target_blocks = (long long)ctx->sm_count * (ctx->knobs[FEO_KNOB_REDUCE_BLOCKS_PER_SM] > 0 ? ctx->knobs[FEO_KNOB_REDUCE_BLOCKS_PER_SM] : 8);
     const int forced = ctx->knobs[FEO_KNOB_REDUCE_SPLIT];
     const bool in_aligned = feo_aligned16(in) && (LOADER == LD_PLAIN || LOADER == LD_VECMAT || feo_aligned16(in2));
@@ -479,8 +543,11 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         which = MICRO;
         const int cands[5] = {2, 4, 8, 16, 32};
         for (int i = 0; i < 5; ++i)
-            if (c.R2 == cands[i] && feo_aligned16(in)) r2c = cands[i];
-        G.xblocks = feo_ceil_div((size_t)c.K2, (size_t)kThreads);
+            if (c.R2 == cands[i] && feo_aligned32(in)) r2c = cands[i];
+        const bool wide = (c.R1 == 1);
+        int outs = r2c == 0 ? 1 : (r2c <= 16 ? 4 : 2);  // MicroShape<R2C, WIDE>::OUTS
+        if (r2c && wide) { outs = 32 / r2c; outs = outs > 8 ? 8 : (outs < 2 ? 2 : outs); }
+        G.xblocks = feo_ceil_div((size_t)c.K2, (size_t)kThreads * outs);
         const long long base_blocks = G.xblocks * c.K1;
         long long S = forced > 0 ? forced : feo_ceil_div((size_t)target_blocks, (size_t)base_blocks);
         S = clampll(S, 1, c.R1 >= 32 ? c.R1 / 16 : 1);
@@ -495,18 +562,22 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         G.lanes = (per_out >= 4096) ? kThreads : 32;
         const long long outs_per_block = kThreads / G.lanes;
         const long long base_blocks = feo_ceil_div((size_t)G.nout, (size_t)outs_per_block);
-        long long S = forced > 0 ? forced : feo_ceil_div((size_t)target_blocks, (size_t)base_blocks);
-        const long long min_elems = 16384;  // keep at least 64 KiB (f32) of work per split
+        const long long want = 4 * target_blocks;  // several waves of small units: no ragged last wave
+        long long S = forced > 0 ? forced : feo_ceil_div((size_t)want, (size_t)base_blocks);
+        const long long min_elems = 4096;  // keep at least 16 KiB (f32) of work per split
         S = clampll(S, 1, per_out / min_elems > 0 ? per_out / min_elems : 1);
         // split rows first, then columns
         long long S1 = S < c.R1 ? S : c.R1;
         G.c1 = feo_ceil_div((size_t)c.R1, (size_t)S1);
         S1 = feo_ceil_div((size_t)c.R1, (size_t)G.c1);
         long long S2 = feo_ceil_div((size_t)S, (size_t)S1);
-        const long long quantum = (long long)G.lanes * 4;  // U vectors per lane per sweep
         long long c2 = feo_ceil_div((size_t)nvec, (size_t)S2);
+        int lx = 1;
+        while (lx < G.lanes && (long long)lx * 4 < c2) lx *= 2;  // U = 4 vectors per lane per sweep
+        const long long quantum = (long long)lx * 4;
         c2 = feo_ceil_div((size_t)c2, (size_t)quantum) * quantum;
         S2 = feo_ceil_div((size_t)nvec, (size_t)c2);
+        G.lx = lx;
         G.S1 = S1; G.S2 = S2; G.S = S1 * S2; G.c2 = c2;
     }
 
@@ -525,7 +596,11 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
     } else if (which == MICRO) {
         const long long blocks = G.xblocks * G.S * c.K1;
         if (blocks > 0x7fffffffLL) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "reduction grid too large");
-#define FEO_MICRO(R) reduce_micro_kernel<T, KIND, R><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, aux, G, divisor, flag)
+#define FEO_MICRO(R)                                                                                                          \
+    do {                                                                                                                      \
+        if (c.R1 == 1) reduce_micro_kernel<T, KIND, R, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, aux, G, divisor, flag); \
+        else reduce_micro_kernel<T, KIND, R, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, aux, G, divisor, flag);        \
+    } while (0)
         switch (r2c) {
         case 2: FEO_MICRO(2); break;
         case 4: FEO_MICRO(4); break;

@@ -285,11 +285,15 @@ def test_broadcast_tile_variants_agree(feo, oracle):
     ta, tb = feo.Tensor(feo.shape(19, 1, 256), a), feo.Tensor(feo.shape(1, 23, 256), b)
     want = oracle.ewise_broadcast("mul", a, b)
     try:
-        for knob in (0, 1, 2, 3, 4):
-            ctx.tune(L.KNOB_BCAST_TILE, knob)
-            np.testing.assert_array_equal(ta.broadcast("mul", tb).to_numpy(), want, err_msg=f"knob {knob}")
+        for knob in (0, 2, 3, 4):
+            for lchunk in (0, 1, 5, 64):
+                ctx.tune(L.KNOB_BCAST_TILE, knob)
+                ctx.tune(L.KNOB_BCAST_LCHUNK, lchunk)
+                np.testing.assert_array_equal(ta.broadcast("mul", tb).to_numpy(), want, err_msg=f"knob {knob} lchunk {lchunk}")
+                np.testing.assert_array_equal(ta.broadcast("sub", tb).to_numpy(), oracle.ewise_broadcast("sub", a, b))
     finally:
         ctx.tune(L.KNOB_BCAST_TILE, 0)
+        ctx.tune(L.KNOB_BCAST_LCHUNK, 0)
 
 
 # ---- reductions ---------------------------------------------------------------------------------------------------
