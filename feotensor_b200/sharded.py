@@ -1,0 +1,278 @@
+"""Leading-axis sharding of the hot path across the GPUs of one node.
+
+One process per GPU (torchrun); `torch.distributed` is the plumbing (NCCL on GPUs, gloo in the CPU tests).
+A ShardedTensor is one dense row-major block of leading rows per rank.  Which ops need an exchange:
+
+  elementwise / scalar / broadcast / outer           none (b with leading extent 1 is replicated)
+  reduce, leading axis kept                           none (result stays sharded)
+  reduce, leading axis removed (or axes == [])        partial per shard, then
+      sum / mean      all-reduce(SUM); mean divides by the GLOBAL counted-in-T divisor afterwards
+      max / min       all-reduce(MAX / MIN)
+      var (floats)    all-gather of per-shard (mean | M2), Chan merge in rank order (deterministic)
+      var (ints)      all-reduce(SUM) -> truncated mean -> squared deviations per shard -> all-reduce -> divide
+  dot                                                 all-reduce(SUM) of per-shard partial dots
+  matmul (A row-sharded)                              none if B is replicated, else all-gather of B
+
+The local arithmetic goes through an *engine*: `CudaEngine` (the C ABI; the only engine this package ships) --
+the CPU tests inject their own checker engine to exercise exactly this exchange logic under gloo.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+class CudaEngine:
+    """Local compute on this rank's GPU through libfeotensor_b200 (arrays are core.Tensor)."""
+
+    def __init__(self, ctx=None):
+        import torch
+
+        from .core import Context
+        self.torch = torch
+        self.ctx = ctx or Context.default()
+        # one stream for the library and for torch's collectives, so NCCL is ordered after the kernels
+        self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    # -- array protocol
+    def dims(self, x):
+        return list(x.shape().dims)
+
+    def dtype(self, x):
+        return x.dtype
+
+    def empty(self, dims, dtype):
+        from .core import Shape, Tensor
+        return Tensor._empty(Shape(list(dims)), dtype, self.ctx)
+
+    def from_host(self, arr):
+        from .core import Shape, Tensor
+        return Tensor(Shape(list(arr.shape)), arr, ctx=self.ctx)
+
+    def as_torch(self, x):
+        """Zero-copy torch view of the device buffer (for the collectives)."""
+        class _CAI:
+            pass
+        obj = _CAI()
+        dt = np.dtype(x.dtype)
+        if dt == np.uint32:
+            dt = np.dtype(np.int32)  # torch collectives lack uint32; callers handle the order-preserving bias
+        obj.__cuda_array_interface__ = {"shape": (x.size(),), "typestr": dt.str, "data": (x.data.ptr, False), "version": 3,
+                                        "strides": None}
+        t = self.torch.as_tensor(obj, device=f"cuda:{self.ctx.device}")
+        t._feo_keepalive = x
+        return t
+
+    # -- local arithmetic
+    def ewise(self, op, a, b):
+        return a._tensor_op(op, b)
+
+    def scalar(self, op, a, s):
+        return a._scalar_op(op, s)
+
+    def broadcast(self, op, a, b):
+        return a.broadcast(op, b)
+
+    def reduce(self, kind, x, axes):
+        return x._reduce(kind, axes)
+
+    def reduce_partial(self, kind, x, axes, nout):
+        """SUM/MEAN -> sums, MAX/MIN -> extrema ([nout]); VAR (floats) -> [2, nout] = means | M2."""
+        ctx, dims = self.ctx, self.dims(x)
+        out = self.empty([2, nout] if kind == "var" else [nout], x.dtype)
+        ctx.check(ctx.lib.feo_reduce_partial(ctx.handle, L.KIND_CODES[kind], x.data.code, C.c_void_p(out.data.ptr),
+                                             C.c_void_p(x.data.ptr), len(dims), L.sizes(dims), len(axes), L.sizes(axes)))
+        return out
+
+    def reduce_sqdev(self, x, mean, axes, nout):
+        ctx, dims = self.ctx, self.dims(x)
+        out = self.empty([nout], x.dtype)
+        ctx.check(ctx.lib.feo_reduce_sqdev(ctx.handle, x.data.code, C.c_void_p(out.data.ptr), C.c_void_p(x.data.ptr),
+                                           C.c_void_p(mean.data.ptr), len(dims), L.sizes(dims), len(axes), L.sizes(axes)))
+        return out
+
+    def var_merge(self, partials, nparts, nout, count_per_part, divisor):
+        ctx = self.ctx
+        out = self.empty([nout], partials.dtype)
+        d = np.array([divisor], dtype=partials.dtype)
+        ctx.check(ctx.lib.feo_var_merge(ctx.handle, partials.data.code, C.c_void_p(out.data.ptr), C.c_void_p(partials.data.ptr),
+                                        nparts, nout, count_per_part, d.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def dot(self, a, b):
+        from .core import Vector
+        return Vector.from_tensor(a).vecmul(Vector.from_tensor(b))._tensor
+
+    def outer(self, a, b):
+        return a.prod(b)
+
+    def matmul(self, A, B, algo="auto"):
+        from .core import Matrix
+        return Matrix.from_tensor(A).matmul(Matrix.from_tensor(B), algo=algo)._tensor
+
+    def reshape(self, x, dims):
+        from .core import Shape, Tensor
+        return Tensor._wrap(Shape(list(dims)), x.data)
+
+
+
+def reduce_divisor(dtype, global_dims, axes):
+    """The reference's counted-in-T divisor for the GLOBAL shape (host-only entry point of the C ABI)."""
+    lib = L.load()
+    out = np.zeros(1, dtype=L.np_dtype(dtype))
+    rc = lib.feo_reduce_divisor(L.code_of(dtype), len(global_dims), L.sizes(global_dims), len(axes), L.sizes(axes),
+                                out.ctypes.data_as(C.c_void_p))
+    if rc != L.OK:
+        raise ValueError("axes must be strictly ascending and in range")
+    return out[0]
+
+
+def reduce_dims(global_dims, axes):
+    lib = L.load()
+    out_rank, out_shape = C.c_int(0), (C.c_size_t * max(len(global_dims), 1))()
+    rc = lib.feo_reduce_shape(len(global_dims), L.sizes(global_dims), len(axes), L.sizes(axes), C.byref(out_rank), out_shape)
+    if rc != L.OK:
+        raise ValueError("axes must be strictly ascending and in range")
+    return [int(out_shape[i]) for i in range(out_rank.value)]
+
+
+class ShardedTensor:
+    """Block `rank` of `world` equal leading-axis blocks of a dense row-major tensor of `global_dims`."""
+
+    def __init__(self, engine, local, global_dims, rank=None, world=None, group=None):
+        dist = _dist()
+        self.engine = engine
+        self.local = local
+        self.global_dims = [int(d) for d in global_dims]
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        if self.global_dims[0] % self.world != 0:
+            raise ValueError(f"leading extent {self.global_dims[0]} is not divisible by {self.world} ranks")
+        want = [self.global_dims[0] // self.world] + self.global_dims[1:]
+        if engine.dims(local) != want:
+            raise ValueError(f"local block has dims {engine.dims(local)}, expected {want}")
+
+    @property
+    def rows_per_rank(self):
+        return self.global_dims[0] // self.world
+
+    def _like(self, local, global_dims=None):
+        return ShardedTensor(self.engine, local, global_dims or self.global_dims, self.rank, self.world, self.group)
+
+    # ---- no-communication ops ---------------------------------------------------------------------------
+    def ewise(self, op, rhs):
+        """Same-shape operator (tensor.rs:362-489); rhs is a ShardedTensor of the same global shape or a scalar."""
+        if isinstance(rhs, ShardedTensor):
+            if rhs.global_dims != self.global_dims:
+                raise ValueError("assertion failed: self.shape == rhs.shape")
+            return self._like(self.engine.ewise(op, self.local, rhs.local))
+        return self._like(self.engine.scalar(op, self.local, rhs))
+
+    def broadcast(self, op, rhs_replicated):
+        """Broadcast against a replicated operand whose leading extent is 1 (config 2: b[1,4096,4096])."""
+        rd = self.engine.dims(rhs_replicated)
+        if len(rd) != len(self.global_dims) or rd[0] != 1:
+            raise ValueError("the replicated operand must have leading extent 1 and the same order")
+        out_local = self.engine.broadcast(op, self.local, rhs_replicated)
+        od = self.engine.dims(out_local)
+        return self._like(out_local, [od[0] * self.world] + od[1:])
+
+    def outer(self, rhs_replicated):
+        """Tensor::prod with a replicated right operand (tensor.rs:311-322): the result is sharded like self."""
+        out_local = self.engine.outer(self.local, rhs_replicated)
+        return self._like(out_local, self.global_dims + self.engine.dims(rhs_replicated))
+
+    def matmul(self, B, b_sharded=False, algo="auto"):
+        """Matrix::matmul with A = self row-sharded (matrix.rs:76-90).  B replicated, or row-sharded -> all-gather."""
+        eng, dist = self.engine, _dist()
+        if len(self.global_dims) != 2:
+            raise ValueError("Shape must have order of 2")
+        if b_sharded:
+            if not isinstance(B, ShardedTensor) or B.global_dims[0] != self.global_dims[1]:
+                raise ValueError("assertion `left == right` failed (inner dimensions)")
+            mine = eng.as_torch(B.local)
+            full = eng.empty(B.global_dims, eng.dtype(B.local))
+            dist.all_gather(list(eng.as_torch(full).view(self.world, -1).unbind(0)), mine, group=self.group)
+            B = full
+        elif eng.dims(B)[0] != self.global_dims[1]:
+            raise ValueError("assertion `left == right` failed (inner dimensions)")
+        out_local = eng.matmul(self.local, B, algo)
+        return self._like(out_local, [self.global_dims[0], eng.dims(B)[1]])
+
+    # ---- reductions ------------------------------------------------------------------------------------------
+    def reduce(self, kind, axes):
+        """Tensor::{sum,mean,var,max,min} (tensor.rs:70-307) on the global tensor.
+
+        Returns a ShardedTensor when the leading axis is kept, else a replicated array (identical on every rank)."""
+        eng, dist = self.engine, _dist()
+        axes = [int(a) for a in axes]
+        out_dims = reduce_dims(self.global_dims, axes)  # validates the axes like the reference would panic
+        if axes and 0 not in axes:
+            out_local = eng.reduce(kind, self.local, axes)
+            return self._like(out_local, out_dims)
+        nout = int(np.prod(out_dims))
+        dtype = np.dtype(eng.dtype(self.local))
+        # axes == [] reduces everything (tensor.rs:84); per shard that is "all local axes"
+        local_axes = axes if axes else list(range(len(self.global_dims)))
+        n_div = reduce_divisor(dtype, self.global_dims, axes)
+        is_float = dtype.kind == "f"
+
+        def allreduce(t, op):
+            if dtype == np.uint32 and op != "sum":  # order-preserving bias for the int32 view
+                t.bitwise_xor_(-2 ** 31)
+            dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN}[op], group=self.group)
+            if dtype == np.uint32 and op != "sum":
+                t.bitwise_xor_(-2 ** 31)
+
+        if kind in ("sum", "mean", "max", "min"):
+            part = eng.reduce_partial(kind, self.local, local_axes, nout)
+            allreduce(eng.as_torch(part), "sum" if kind in ("sum", "mean") else kind)
+            if kind == "mean":
+                part = eng.scalar("div", part, n_div)
+            return eng.reshape(part, out_dims)
+        if kind != "var":
+            raise ValueError(f"unknown reduction {kind}")
+        local_count = int(np.prod([eng.dims(self.local)[a] for a in local_axes]))
+        if is_float:
+            part = eng.reduce_partial("var", self.local, local_axes, nout)  # [2, nout]
+            gathered = part
+            if self.world > 1:
+                gathered = eng.empty([self.world, 2, nout], dtype)
+                dist.all_gather(list(eng.as_torch(gathered).view(self.world, -1).unbind(0)), eng.as_torch(part), group=self.group)
+            merged = eng.var_merge(gathered, self.world, nout, local_count, n_div)
+            return eng.reshape(merged, out_dims)
+        # integers: the reference's own two-pass scheme, exactly (tensor.rs:171-177, 188, 196-202)
+        total = eng.reduce_partial("sum", self.local, local_axes, nout)
+        allreduce(eng.as_torch(total), "sum")
+        mean = eng.scalar("div", total, n_div)
+        sq = eng.reduce_sqdev(self.local, mean, local_axes, nout)
+        allreduce(eng.as_torch(sq), "sum")
+        return eng.reshape(eng.scalar("div", sq, n_div), out_dims)
+
+    def dot(self, rhs):
+        """Vector::vecmul (vector.rs:71-78) on two identically sharded vectors: a replicated [1] result."""
+        eng = self.engine
+        if rhs.global_dims != self.global_dims or len(self.global_dims) != 1:
+            raise ValueError("assertion failed: self.shape() == rhs.shape()")
+        part = eng.dot(self.local, rhs.local)
+        _dist().all_reduce(eng.as_torch(part), group=self.group)
+        return part
+
+
+def shard_rows(engine, full_host: np.ndarray, rank=None, world=None, group=None):
+    """Upload this rank's block of leading rows of a host array (test / example helper)."""
+    dist = _dist()
+    rank = dist.get_rank(group) if rank is None else rank
+    world = dist.get_world_size(group) if world is None else world
+    rows = full_host.shape[0] // world
+    block = np.ascontiguousarray(full_host[rank * rows:(rank + 1) * rows])
+    return ShardedTensor(engine, engine.from_host(block), list(full_host.shape), rank, world, group)
