@@ -304,7 +304,7 @@ int feo_matmul(feo_ctx *ctx, int algo, int dtype, void *C, const void *A, const 
     if (algo == FEO_MATMUL_TF32X3) {
         if (dtype != FEO_F32) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "TF32X3 is f32-only");
         if (!feo_matmul_tf32x3_supported(M, K, N))
-            return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "TF32X3 needs M%%128==0, N%%128==0, K%%32==0");
+            return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "TF32X3 is used for M*N*K >= 2^21 (smaller products run on the SIMT kernel)");
         return feo_impl_matmul_tf32x3(ctx, C, A, B, M, K, N);
     }
     if (algo != FEO_MATMUL_SIMT) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "unknown matmul algo %d", algo);

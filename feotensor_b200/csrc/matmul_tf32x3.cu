@@ -1,10 +1,353 @@
-// matmul_tf32x3.cu -- K7: DynamicMatrix::matmul (matrix.rs:76-90) for f32 on the tcgen05 tensor cores
-// with split-TF32 (3xTF32).  Placeholder until the tcgen05/TMEM/TMA kernel lands: reports the
-// algorithm as unavailable so FEO_MATMUL_AUTO resolves to the SIMT kernel.
+// matmul_tf32x3.cu -- K7: DynamicMatrix::matmul (matrix.rs:76-90) for f32 on the 5th-generation tensor cores.
+//
+//   C[M,N] = A[M,K] * B[K,N]  (all dense row-major f32), computed as split-TF32 ("3xTF32"):
+//       a = a_hi + a_lo,  a_hi = rna_tf32(a),  a_lo = a - a_hi   (exact in f32; the MMA reads a_lo's top 19 bits)
+//       C = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi                    (small terms first; A_lo*B_lo ~ 2^-22 is dropped)
+//   with f32 accumulation in tensor memory.  Error ~ 1e-6 * sum|a||b|: inside the f32 reassociation bound the
+//   reference's own sequential sum obeys, at 3 tensor-core passes instead of the FP32 SIMT pipe.
+//
+// Structure (hand-written PTX; no CUTLASS):
+//   pre-pass   split_rows_kernel     A  -> A_hi, A_lo          [M,K]  (K-major as is)
+//              split_transpose_kernel B -> Bt_hi, Bt_lo        [N,K]  (transposed so both operands are K-major)
+//              ~1.5 GiB of traffic for 8192^3 (0.25 ms) against milliseconds of MMA time.
+//   main       matmul_tf32x3_kernel  one 128 x 256 output tile per CTA, BK = 32 (one 128-byte swizzle atom):
+//              warp 0   TMA producer: cp.async.bulk.tensor (128B swizzle) of A_hi/A_lo/Bt_hi/Bt_lo k-blocks into a
+//                       kStages-deep shared-memory ring, completion on mbarriers (expect_tx)
+//              warp 1   allocates all 512 TMEM columns (two 128x256 f32 accumulators); one lane issues
+//                       tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=256, K=8; 12 per k-block) from shared-memory
+//                       descriptors; tcgen05.commit frees the ring slot / publishes a finished chunk
+//              warps 2-9 accumulate + epilogue.  The tensor core TRUNCATES when it adds into the TMEM accumulator
+//                       (measured: 83 % of the errors point toward zero and the bias grows linearly with K,
+//                       -1.7e-4 relative at K = 16384 on positive data), so K is cut into chunks of kc k-blocks that
+//                       accumulate into alternating TMEM buffers; these warps drain each finished chunk with
+//                       tcgen05.ld (32x32b.x32) and add it to f32 registers with round-to-nearest, overlapped with
+//                       the MMAs of the next chunk, then write C.
+// Bound: the tensor pipe (3 x 2MNK TF32 flop) -- and, with f32 operands split in two, the L2->SM operand stream
+// (96 KiB per k-block per CTA); see DESIGN.md 4.6 for the measured utilisation.
+#include <cuda.h>
+
 #include "feo_common.cuh"
 
-bool feo_matmul_tf32x3_supported(size_t, size_t, size_t) { return false; }
+namespace {
 
-int feo_impl_matmul_tf32x3(feo_ctx *ctx, void *, const void *, const void *, size_t, size_t, size_t) {
-    return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "TF32X3 matmul is not built into this library yet");
+constexpr int BM = 128, BN = 256, BK = 32;      // CTA tile; BK floats = 128 bytes = one swizzle atom row
+constexpr int UMMA_K = 8;                        // tf32: 32 bytes of K per instruction
+constexpr int kStages = 2;
+constexpr int kTileABytes = BM * BK * 4;         // 16 KiB
+constexpr int kTileBBytes = BN * BK * 4;         // 32 KiB
+constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;  // hi + lo of both operands: 96 KiB
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int kThreads = 320;                    // warp 0 TMA, warp 1 MMA, warps 2..9 accumulate + epilogue
+constexpr int kTmemCols = 512;                   // two accumulator buffers of BN columns
+constexpr int kEpiWarps = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a pipeline bug traps (and reports) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int what) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spin > 20000000u) {
+            printf("matmul_tf32x3: mbarrier wait timed out (what=%d block=%d,%d thread=%d parity=%u)\n", what, blockIdx.x, blockIdx.y,
+                   threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// K-major, 128-byte swizzle shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024 bytes apart).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset: next 8-row group
+    d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+    return d;
+}
+// kind::tf32, f32 accumulate, both operands K-major, M = 128, N = 256.
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+matmul_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                     float *__restrict__ C, int M, int N, int num_k_blocks, int kc) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+    uint64_t *empty_bar = full_bar + kStages;
+    uint64_t *tmem_full_bar = empty_bar + kStages;   // [2]: chunk accumulated in buffer b
+    uint64_t *tmem_empty_bar = tmem_full_bar + 2;    // [2]: buffer b drained by all epilogue warps
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int num_chunks = (num_k_blocks + kc - 1) / kc;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
+    }
+    if (warp == 1) {  // whole warp: allocate the accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1, 0);
+                uint8_t *st = smem + s * kStageBytes;
+                mbar_expect_tx(&full_bar[s], kStageBytes);
+                tma_load_2d(st, &map_a_hi, &full_bar[s], kb * BK, m0);
+                tma_load_2d(st + kTileABytes, &map_a_lo, &full_bar[s], kb * BK, m0);
+                tma_load_2d(st + 2 * kTileABytes, &map_b_hi, &full_bar[s], kb * BK, n0);
+                tma_load_2d(st + 2 * kTileABytes + kTileBBytes, &map_b_lo, &full_bar[s], kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            int kb = 0;
+            for (int c = 0; c < num_chunks; ++c) {
+                const int buf = c & 1;
+                mbar_wait(&tmem_empty_bar[buf], ((c >> 1) & 1) ^ 1, 3);  // the epilogue has drained this buffer
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+                const int kb_end = (kb + kc < num_k_blocks) ? kb + kc : num_k_blocks;
+                for (int first = 1; kb < kb_end; ++kb) {
+                    const int s = kb % kStages;
+                    const uint32_t ph = (kb / kStages) & 1;
+                    mbar_wait(&full_bar[s], ph, 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = smem_u32(smem + s * kStageBytes);
+                    const uint64_t da_hi = make_desc(st), da_lo = make_desc(st + kTileABytes);
+                    const uint64_t db_hi = make_desc(st + 2 * kTileABytes), db_lo = make_desc(st + 2 * kTileABytes + kTileBBytes);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // 32 bytes per step, in 16-byte units
+                        umma_tf32(tmem_d, da_lo + adv, db_hi + adv, first ? 0u : 1u);  // the chunk's first MMA overwrites
+                        first = 0;
+                        umma_tf32(tmem_d, da_hi + adv, db_lo + adv, 1);
+                        umma_tf32(tmem_d, da_hi + adv, db_hi + adv, 1);
+                    }
+                    umma_commit(&empty_bar[s]);  // frees the ring slot once these MMAs have read it
+                }
+                umma_commit(&tmem_full_bar[buf]);  // chunk complete in TMEM
+            }
+        }
+    } else {  // ===== accumulate + epilogue: warps 2..9; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
+        const int q = warp & 3;                 // lane quarter
+        const int half = (warp - 2) >> 2;       // which 128 of the 256 accumulator columns
+        float acc[BN / 2];
+#pragma unroll
+        for (int i = 0; i < BN / 2; ++i) acc[i] = 0.f;
+        for (int c = 0; c < num_chunks; ++c) {
+            const int buf = c & 1;
+            mbar_wait(&tmem_full_bar[buf], (c >> 1) & 1, 2);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < BN / 2; j += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * (BN / 2) + j);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                      "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                      "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[j + i] += __uint_as_float(v[i]);  // round-to-nearest f32 add
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        }
+        // ragged edges: TMA zero-filled the out-of-range rows of A / Bt, so acc is well defined everywhere; only
+        // the stores are guarded (128-bit when the row start is 16-byte aligned, i.e. N % 4 == 0)
+        const int row = m0 + q * 32 + lane;
+        const int col0 = n0 + half * (BN / 2);
+        if (row < M) {
+            float *crow = C + (size_t)row * N + col0;
+            if ((N & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < BN / 2; j += 4)
+                    if (col0 + j < N) *reinterpret_cast<float4 *>(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < BN / 2; ++j)
+                    if (col0 + j < N) crow[j] = acc[j];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- pre-pass: hi/lo split --------------------------------------------------------------------------------
+__device__ __forceinline__ void split1(float x, float &hi, float &lo) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    lo = x - hi;
+}
+// A[M,K] -> hi/lo [M,Kp] (Kp = K rounded up to BK, zero padded).
+__global__ void __launch_bounds__(256) split_rows_kernel(float *__restrict__ hi, float *__restrict__ lo, const float *__restrict__ x, int M, int K, int Kp, bool vec) {
+    const size_t nvec = (size_t)M * (Kp / 4);
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (size_t)gridDim.x * 256) {
+        const size_t m = i / (Kp / 4);
+        const int k = (int)(i % (Kp / 4)) * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec && k + 3 < K) {
+            const float4 t = *reinterpret_cast<const float4 *>(x + m * K + k);
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k + j < K) v[j] = x[m * K + k + j];
+        }
+        float4 h, l;
+        split1(v[0], h.x, l.x); split1(v[1], h.y, l.y); split1(v[2], h.z, l.z); split1(v[3], h.w, l.w);
+        reinterpret_cast<float4 *>(hi)[i] = h;
+        reinterpret_cast<float4 *>(lo)[i] = l;
+    }
+}
+// B[K,N] -> hi/lo [N,Kp] through a padded 32x32 shared tile (coalesced on both sides); zero beyond K.
+__global__ void __launch_bounds__(256) split_transpose_kernel(float *__restrict__ hi, float *__restrict__ lo, const float *__restrict__ b, int K, int N, int Kp) {
+    __shared__ float tile[32][33];
+    const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) tile[r][tx] = (k0 + r < K && n0 + tx < N) ? b[(size_t)(k0 + r) * N + n0 + tx] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        if (n0 + r < N) {  // k0 + tx < Kp always (Kp is a multiple of 32)
+            float h, l;
+            split1(tile[tx][r], h, l);
+            hi[(size_t)(n0 + r) * Kp + k0 + tx] = h;
+            lo[(size_t)(n0 + r) * Kp + k0 + tx] = l;
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D row-major [rows, K] f32 tensor, box = BK x box_rows, 128-byte swizzle.
+bool make_map(CUtensorMap *map, const float *base, size_t rows, size_t K, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool feo_matmul_tf32x3_supported(size_t M, size_t K, size_t N) {
+    // any shape works (ragged edges are zero-filled / guarded); tiny products stay on the SIMT kernel, which is
+    // launch-bound there anyway and keeps the k-order of the reference
+    const size_t lim = size_t(1) << 31;
+    return M >= 1 && N >= 1 && K >= 1 && M < lim && N < lim && K < lim - BK && (M + BM - 1) / BM <= 65535 && M * N * K >= (size_t(1) << 21);
+}
+
+int feo_impl_matmul_tf32x3(feo_ctx *ctx, void *C, const void *A, const void *B, size_t M, size_t K, size_t N) {
+    if (!feo_aligned16(A) || !feo_aligned16(B) || !feo_aligned16(C)) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "TF32X3 needs 16-byte aligned operands");
+    static bool attr_set = false;
+    if (!attr_set) {
+        FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        attr_set = true;
+    }
+    // workspace: A_hi | A_lo [M,Kp]  and  Bt_hi | Bt_lo [N,Kp], Kp = K rounded up to one k-block
+    const size_t Kp = (K + BK - 1) / BK * BK;
+    void *ws = nullptr;
+    const size_t a_elems = M * Kp, b_elems = N * Kp;
+    int rc = feo_workspace(ctx, (2 * a_elems + 2 * b_elems) * sizeof(float), &ws);
+    if (rc != FEO_OK) return rc;
+    float *a_hi = (float *)ws, *a_lo = a_hi + a_elems, *b_hi = a_lo + a_elems, *b_lo = b_hi + b_elems;
+
+    size_t blocks = feo_ceil_div(a_elems / 4, (size_t)256);
+    if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
+    split_rows_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a_hi, a_lo, (const float *)A, (int)M, (int)K, (int)Kp, K % 4 == 0);
+    FEO_LAUNCH_CHECK(ctx);
+    split_transpose_kernel<<<dim3((unsigned)feo_ceil_div(N, (size_t)32), (unsigned)(Kp / 32)), 256, 0, ctx->stream>>>(b_hi, b_lo, (const float *)B, (int)K, (int)N, (int)Kp);
+    FEO_LAUNCH_CHECK(ctx);
+
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    if (!make_map(&ma_hi, a_hi, M, Kp, BM) || !make_map(&ma_lo, a_lo, M, Kp, BM) || !make_map(&mb_hi, b_hi, N, Kp, BN) ||
+        !make_map(&mb_lo, b_lo, N, Kp, BN))
+        return feo_fail(ctx, FEO_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    const dim3 grid((unsigned)feo_ceil_div(N, (size_t)BN), (unsigned)feo_ceil_div(M, (size_t)BM));
+    int kc = ctx->knobs[FEO_KNOB_MATMUL_TF32_KC];
+    if (kc <= 0) kc = 2;  // k-blocks per TMEM accumulation chain (24 truncating accumulates), see the file header
+    matmul_tf32x3_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, (float *)C, (int)M, (int)N, (int)(Kp / BK), kc);
+    FEO_LAUNCH_CHECK(ctx);
+    return FEO_OK;
 }

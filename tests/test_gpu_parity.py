@@ -496,3 +496,41 @@ def test_device_generator_matches_host_twin(feo, oracle):
     # strided regeneration of single columns
     np.testing.assert_array_equal(oracle.fill_uniform("f32", 10, 42, 5, -1, 1, stride=37),
                                   oracle.fill_uniform("f32", 37 * 10, 42, 0, -1, 1)[5::37])
+
+
+TF32X3_CASES = [(128, 256, 256), (256, 96, 512), (128, 4096, 256), (384, 1024, 768), (1024, 1024, 1024),
+                (130, 70, 257), (100, 1000, 300), (1, 3000, 1000), (257, 33, 513), (511, 129, 255), (64, 4099, 64)]  # ragged edges
+
+
+def test_matmul_tf32x3_vs_oracle(feo, oracle):
+    """tcgen05 split-TF32 matmul: |gpu - exact| <= max(2*|ref - exact|, 2^-20 * sum|a||b|), where ref is
+    the oracle's sequential f32 result and exact the f64 product; also inside the generic reassociation bound."""
+    rng = np.random.default_rng(700)
+    for m, k, n in TF32X3_CASES:
+        A, B = rand(oracle, rng, "f32", (m, k)), rand(oracle, rng, "f32", (k, n))
+        tA, tB = feo.Matrix(feo.shape(m, k), A), feo.Matrix(feo.shape(k, n), B)
+        got = tA.matmul(tB, algo="tf32x3").to_numpy()
+        exact = A.astype(np.float64) @ B.astype(np.float64)
+        terms = np.abs(A.astype(np.float64)) @ np.abs(B.astype(np.float64))
+        err = np.abs(got - exact)
+        if m * k * n <= 384 * 1024 * 768:
+            ref = oracle.matmul(A, B)
+            bound = np.maximum(2 * np.abs(ref - exact), 2.0 ** -20 * terms)
+            assert np.all(err <= bound), f"{m}x{k}x{n}: max err {err.max():.3e}, worst ratio {(err / bound).max():.2f}"
+            assert_sum_like(got, ref, terms, k + 1, "f32", f"tf32x3 {m}x{k}x{n}")
+        assert np.all(err <= 2.0 ** -20 * terms), f"{m}x{k}x{n}: max rel err {(err / terms).max():.3e}"
+        # AUTO picks the tensor-core path for supported f32 shapes and agrees with it bit for bit
+        np.testing.assert_array_equal(tA.matmul(tB).to_numpy(), got)
+    # exact small-integer data: every product and partial sum is exact in TF32 x f32
+    A = rng.integers(-8, 9, (128, 64)).astype(np.float32)
+    B = rng.integers(-8, 9, (64, 256)).astype(np.float32)
+    got = feo.Matrix(feo.shape(128, 64), A).matmul(feo.Matrix(feo.shape(64, 256), B), algo="tf32x3").to_numpy()
+    np.testing.assert_array_equal(got, A @ B)
+    # long K on positive data: the chunked accumulation keeps the tensor core's truncation bias from growing with K
+    A, B = np.abs(rand(oracle, rng, "f32", (128, 16384))), np.abs(rand(oracle, rng, "f32", (16384, 256)))
+    got = feo.Matrix(feo.shape(128, 16384), A).matmul(feo.Matrix(feo.shape(16384, 256), B), algo="tf32x3").to_numpy()
+    exact = A.astype(np.float64) @ B.astype(np.float64)
+    assert np.max(np.abs(got - exact) / exact) < 3e-6
+    # tiny products are refused for the explicit algorithm (AUTO runs them on the SIMT kernel)
+    with pytest.raises(feo.BackendError):
+        feo.Matrix(feo.shape(4, 4), np.zeros(16, np.float32)).matmul(feo.Matrix(feo.shape(4, 4), np.zeros(16, np.float32)), algo="tf32x3")

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--split", type=int, default=0)
     ap.add_argument("--bpsm", type=int, default=0)
     ap.add_argument("--lchunk", type=int, default=0)
+    ap.add_argument("--kc", type=int, default=0)
     args = ap.parse_args()
 
     import torch
@@ -49,6 +50,7 @@ def main():
     ctx.tune(L.KNOB_REDUCE_SPLIT, args.split)
     ctx.tune(L.KNOB_REDUCE_BLOCKS_PER_SM, args.bpsm)
     ctx.tune(L.KNOB_BCAST_LCHUNK, args.lchunk)
+    ctx.tune(L.KNOB_MATMUL_TF32_KC, args.kc)
     lib, h, vp = ctx.lib, ctx.handle, C.c_void_p
     dt = L.code_of(args.dtype)
     es = L.np_dtype(args.dtype).itemsize
@@ -119,7 +121,7 @@ def main():
         A, B, Cm = dev(m * m), dev(m * m), dev(m * m)
         fill(A, m * m, 8); fill(B, m * m, 9)
         timed(lambda: ctx.check(lib.feo_matmul(h, L.ALGO_CODES[args.algo], dt, vp(Cm.data_ptr()), vp(A.data_ptr()), vp(B.data_ptr()), m, m, m)),
-              f"matmul {m}^3 {args.algo}", flop=2.0 * m ** 3)
+              f"matmul {m}^3 {args.algo} kc={args.kc}", flop=2.0 * m ** 3)
     elif args.case == "ceilings":
         # library kernels as yardsticks (not product): pure write, pure read, copy
         n = 1 << 28
@@ -128,6 +130,15 @@ def main():
         timed(lambda: x.zero_(), "torch zero_ 1 GiB (pure write)", nbytes=4 * n)
         timed(lambda: y.copy_(x), "torch copy_ 1 GiB (read+write)", nbytes=8 * n)
         timed(lambda: x.sum(), "torch sum 1 GiB (pure read)", nbytes=4 * n)
+        del x, y
+        m = 8192
+        A = torch.randn(m, m, device="cuda"); B = torch.randn(m, m, device="cuda")
+        torch.backends.cuda.matmul.allow_tf32 = True
+        timed(lambda: torch.matmul(A, B), "cuBLAS tf32 8192^3 (1 pass: the TF32 pipe yardstick)", flop=2.0 * m ** 3)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        timed(lambda: torch.matmul(A, B), "cuBLAS fp32 8192^3", flop=2.0 * m ** 3)
+        Ab, Bb = A.bfloat16(), B.bfloat16()
+        timed(lambda: torch.matmul(Ab, Bb), "cuBLAS bf16 8192^3", flop=2.0 * m ** 3)
     elif args.case == "ewise":
         n = args.n
         x, y, o = dev(n), dev(n), dev(n)
