@@ -233,6 +233,15 @@ def run_suite(torch, feo, L, ctx, hbm_peak, tf_peak):
     A, B, Cm = dev(4 * m * m), dev(4 * m * m), dev(4 * m * m)
     fill(A, m * m, SEED + 40); fill(B, m * m, SEED + 41)
     flop = 2.0 * m ** 3
+    # yardstick only (library GEMM, not product): cuBLAS single-pass TF32 = what the TF32 pipe delivers on this box
+    At, Bt = torch.empty(m, m, device="cuda"), torch.empty(m, m, device="cuda")
+    fill(At, m * m, SEED + 42); fill(Bt, m * m, SEED + 43)  # same uniform data as the product (power is data dependent)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    tf32_yard = flop / timed(torch, lambda: torch.matmul(At, Bt), 5, 2) / 1e9
+    torch.backends.cuda.matmul.allow_tf32 = old
+    suite["C4_yardstick_cublas_tf32_1pass"] = {"TFLOP/s": round(tf32_yard, 1), "note": "library kernel, denominator for the TF32 pipe"}
+    del At, Bt
     for algo in ("simt", "tf32x3"):
         rc = ctx.lib.feo_matmul(ctx.handle, L.ALGO_CODES[algo], L.F32, vp(Cm.data_ptr()), vp(A.data_ptr()), vp(B.data_ptr()), m, m, m)
         if rc != L.OK:
@@ -243,7 +252,10 @@ def run_suite(torch, feo, L, ctx, hbm_peak, tf_peak):
         tf = flop / ms / 1e9
         entry = {"ms": round(ms, 3), "TFLOP/s": round(tf, 2)}
         if algo == "tf32x3":
-            entry["tf32_pipe_util_of_bf16_half"] = round(3 * tf / (tf_peak / 2), 3)
+            entry["tf32_pipe_TFLOP/s"] = round(3 * tf, 1)  # three TF32 MMAs per logical product
+            entry["tf32_pipe_util_vs_cublas_tf32"] = round(3 * tf / tf32_yard, 3)
+            entry["tf32_pipe_util_vs_bf16_peak_half"] = round(3 * tf / (tf_peak / 2), 3)
+            entry["includes"] = "hi/lo split pre-pass (2 launches) + tcgen05 kernel"
         else:
             entry["frac_fp32_simt_peak_74.4"] = round(tf / 74.4, 3)
         suite[f"C4_matmul_{algo}"] = entry

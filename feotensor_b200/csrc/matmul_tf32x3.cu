@@ -40,6 +40,7 @@ constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 
 constexpr int kThreads = 320;                    // warp 0 TMA, warp 1 MMA, warps 2..9 accumulate + epilogue
 constexpr int kTmemCols = 512;                   // two accumulator buffers of BN columns
 constexpr int kEpiWarps = 8;
+constexpr int kGroupM = 16;                      // rasterisation group (tiles along M)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -66,7 +67,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int wh
             : "memory");
         if (done) return;
         if (spin > 20000000u) {
-            printf("matmul_tf32x3: mbarrier wait timed out (what=%d block=%d,%d thread=%d parity=%u)\n", what, blockIdx.x, blockIdx.y,
+            printf("matmul_tf32x3: mbarrier wait timed out (what=%d block=%d,%d thread=%d parity=%u)\n", what, blockIdx.x, 0,
                    threadIdx.x, parity);
             __trap();
         }
@@ -116,7 +117,18 @@ matmul_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    // grouped rasterisation: consecutive CTAs walk kGroupM tiles down M before moving along N, so one wave of 148 CTAs
+    // touches a near-square (16 x ~9 tiles) region: half the DRAM operand traffic of row-major order (ncu: 8.2 -> ~4 GB)
+    const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    int pid_m, pid_n;
+    {
+        const int pid = blockIdx.x, in_group = kGroupM * tiles_n;
+        const int first_m = (pid / in_group) * kGroupM;
+        const int group_m = (tiles_m - first_m < kGroupM) ? tiles_m - first_m : kGroupM;
+        pid_m = first_m + (pid % in_group) % group_m;
+        pid_n = (pid % in_group) / group_m;
+    }
+    const int m0 = pid_m * BM, n0 = pid_n * BN;
     const int num_chunks = (num_k_blocks + kc - 1) / kc;
 
     if (warp == 0 && lane == 0) {
@@ -315,7 +327,7 @@ bool feo_matmul_tf32x3_supported(size_t M, size_t K, size_t N) {
     // any shape works (ragged edges are zero-filled / guarded); tiny products stay on the SIMT kernel, which is
     // launch-bound there anyway and keeps the k-order of the reference
     const size_t lim = size_t(1) << 31;
-    return M >= 1 && N >= 1 && K >= 1 && M < lim && N < lim && K < lim - BK && (M + BM - 1) / BM <= 65535 && M * N * K >= (size_t(1) << 21);
+    return M >= 1 && N >= 1 && K >= 1 && M < lim && N < lim && K < lim - BK && M * N * K >= (size_t(1) << 21);
 }
 
 int feo_impl_matmul_tf32x3(feo_ctx *ctx, void *C, const void *A, const void *B, size_t M, size_t K, size_t N) {
@@ -344,7 +356,9 @@ int feo_impl_matmul_tf32x3(feo_ctx *ctx, void *C, const void *A, const void *B, 
     if (!make_map(&ma_hi, a_hi, M, Kp, BM) || !make_map(&ma_lo, a_lo, M, Kp, BM) || !make_map(&mb_hi, b_hi, N, Kp, BN) ||
         !make_map(&mb_lo, b_lo, N, Kp, BN))
         return feo_fail(ctx, FEO_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-    const dim3 grid((unsigned)feo_ceil_div(N, (size_t)BN), (unsigned)feo_ceil_div(M, (size_t)BM));
+    const size_t tiles = feo_ceil_div(N, (size_t)BN) * feo_ceil_div(M, (size_t)BM);
+    if (tiles > 0x7fffffffu) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "matmul grid too large");
+    const dim3 grid((unsigned)tiles);
     int kc = ctx->knobs[FEO_KNOB_MATMUL_TF32_KC];
     if (kc <= 0) kc = 2;  // k-blocks per TMEM accumulation chain (24 truncating accumulates), see the file header
     matmul_tf32x3_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, (float *)C, (int)M, (int)N, (int)(Kp / BK), kc);
