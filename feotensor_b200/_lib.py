@@ -61,6 +61,7 @@ SIGNATURES = {
     "feo_fill_uniform": (_int, [_vp, _int, _vp, _sz, C.c_uint64, C.c_uint64, C.c_double, C.c_double]),
     "feo_ewise": (_int, [_vp, _int, _int, _vp, _vp, _vp, _sz]),
     "feo_ewise_scalar": (_int, [_vp, _int, _int, _vp, _vp, _vp, _sz]),
+    "feo_pow": (_int, [_vp, _int, _vp, _vp, _vp, _sz]),
     "feo_ewise_broadcast": (_int, [_vp, _int, _int, _vp, _vp, _vp, _int, _szp, _szp, _szp]),
     "feo_arith_flag": (_int, [_vp, C.POINTER(_int), _int]),
     "feo_reduce": (_int, [_vp, _int, _int, _vp, _vp, _int, _szp, _int, _szp]),

@@ -433,6 +433,40 @@ class Tensor:
                                     self.size(), C.c_void_p(other.data.ptr), other.size()))
         return out
 
+    def pow(self, power) -> "Tensor":
+        """Elementwise powf, Float element types only (tensor.rs:325-333)."""
+        if self.dtype.kind != "f":
+            raise TypeError("pow needs a Float element type (tensor.rs:325)")
+        ctx = self.ctx
+        out = Tensor._empty(self._shape, self.dtype, ctx)
+        p = np.array([power], dtype=self.dtype)
+        ctx.check(ctx.lib.feo_pow(ctx.handle, self.data.code, C.c_void_p(out.data.ptr), C.c_void_p(self.data.ptr),
+                                  p.ctypes.data_as(C.c_void_p), self.size()))
+        return out
+
+    def display(self) -> str:
+        """Nested-bracket rendering (tensor.rs:507-551); host-side formatting of a downloaded copy."""
+        def item(x):
+            if self.dtype.kind != "f":
+                return str(int(x))
+            if np.isnan(x):
+                return "NaN"
+            if np.isinf(x):
+                return "inf" if x > 0 else "-inf"
+            return np.format_float_positional(x, unique=True, trim="-")  # Rust's `{}`: shortest round-trip, no exponent
+
+        def fmt(data, dims, level):
+            if len(dims) == 1:
+                return "[" + ", ".join(item(x) for x in data) + "]"
+            sub = int(np.prod(dims[1:]))
+            parts = []
+            for i in range(dims[0]):
+                lead = "" if i == 0 else ",\n" + "\n" * (len(dims) - 2) + " " * level
+                parts.append(lead + fmt(data[i * sub:(i + 1) * sub], dims[1:], level + 1))
+            return "[" + "".join(parts) + "]"
+
+        return fmt(self.data.to_numpy(), list(self._shape.dims), 1)
+
     # elementwise operators (tensor.rs:336-505)
     def _scalar_op(self, op: str, rhs):
         ctx = self.ctx
@@ -551,6 +585,13 @@ class _Wrapper:
 
     def prod(self, other):
         return self._tensor.prod(other)
+
+    def pow(self, power):
+        """matrix.rs:106-110 / vector.rs:94-98."""
+        return type(self).from_tensor(self._tensor.pow(power))
+
+    def display(self):
+        return self._tensor.display()
 
     def to_numpy(self):
         return self._tensor.to_numpy()

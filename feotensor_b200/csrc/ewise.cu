@@ -61,7 +61,40 @@ __global__ void __launch_bounds__(kThreads) fill_uniform_kernel(T *__restrict__ 
     }
 }
 
+// Tensor::pow (tensor.rs:325-333).  mode: 0 generic powf, 1 x*x, 2 x, 3 sqrt, 4 one, 5 1/x.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) pow_kernel(T *__restrict__ out, const T *__restrict__ a, T power, int mode, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        const T x = a[i];
+        T r;
+        switch (mode) {
+        case 1: r = x * x; break;
+        case 2: r = x; break;
+        case 3: r = sqrt(x); break;
+        case 4: r = (T)1; break;
+        case 5: r = (T)1 / x; break;
+        default: r = pow(x, power); break;
+        }
+        out[i] = r;
+    }
+}
+
 }  // namespace
+
+int feo_impl_pow(feo_ctx *ctx, int dtype, void *out, const void *a, const void *power_host, size_t n) {
+    size_t blocks = feo_ceil_div(n, (size_t)kThreads);
+    if (blocks > (size_t)ctx->sm_count * 32) blocks = (size_t)ctx->sm_count * 32;
+    auto mode_of = [](double p) { return p == 2.0 ? 1 : p == 1.0 ? 2 : p == 0.5 ? 3 : p == 0.0 ? 4 : p == -1.0 ? 5 : 0; };
+    if (dtype == FEO_F32) {
+        const float p = *(const float *)power_host;
+        pow_kernel<float><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>((float *)out, (const float *)a, p, mode_of(p), n);
+    } else {
+        const double p = *(const double *)power_host;
+        pow_kernel<double><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>((double *)out, (const double *)a, p, mode_of(p), n);
+    }
+    FEO_LAUNCH_CHECK(ctx);
+    return FEO_OK;
+}
 
 int feo_impl_fill_uniform(feo_ctx *ctx, int dtype, void *out, size_t n, uint64_t seed, uint64_t first_index, double lo, double hi) {
     size_t blocks = feo_ceil_div(n, (size_t)kThreads);

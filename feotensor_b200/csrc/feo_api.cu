@@ -212,6 +212,12 @@ int feo_ewise_scalar(feo_ctx *ctx, int op, int dtype, void *out, const void *a, 
     if (n == 0) return FEO_OK;
     return feo_impl_ewise(ctx, op, dtype, out, a, nullptr, scalar_host, n);
 }
+int feo_pow(feo_ctx *ctx, int dtype, void *out, const void *a, const void *power_host, size_t n) {
+    if (!ctx || !out || !a || !power_host) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
+    if (dtype != FEO_F32 && dtype != FEO_F64) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "pow needs a Float element type (tensor.rs:325)");
+    if (n == 0) return FEO_OK;
+    return feo_impl_pow(ctx, dtype, out, a, power_host, n);
+}
 int feo_ewise_broadcast(feo_ctx *ctx, int op, int dtype, void *out, const void *a, const void *b, int rank,
                         const size_t *shape, const size_t *sa, const size_t *sb) {
     if (!ctx || !out || !a || !b) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");

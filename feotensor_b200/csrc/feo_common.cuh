@@ -174,6 +174,7 @@ int feo_impl_ewise(feo_ctx *ctx, int op, int dtype, void *out, const void *a, co
 int feo_impl_broadcast(feo_ctx *ctx, int op, int dtype, void *out, const void *a, const void *b, int rank,
                        const size_t *shape, const size_t *sa, const size_t *sb);
 int feo_impl_fill(feo_ctx *ctx, int dtype, void *out, const void *value, size_t n);
+int feo_impl_pow(feo_ctx *ctx, int dtype, void *out, const void *a, const void *power_host, size_t n);
 int feo_impl_eye(feo_ctx *ctx, int dtype, void *out, size_t rows, size_t cols);
 int feo_impl_fill_uniform(feo_ctx *ctx, int dtype, void *out, size_t n, uint64_t seed, uint64_t first_index, double lo, double hi);
 

@@ -234,6 +234,12 @@ public:
     Tensor max(const Axes &axes) const { return reduce(FEO_MAX, axes); }
     Tensor min(const Axes &axes) const { return reduce(FEO_MIN, axes); }
 
+    Tensor pow(T power) const {  // tensor.rs:325-333 (Float element types only)
+        static_assert(std::is_floating_point<T>::value, "pow needs a Float element type (tensor.rs:325)");
+        Tensor out(shape_, DeviceStorage<T>(data_.ctx(), size()));
+        ctx().check(feo_pow(ctx().raw(), DT, out.ptr(), ptr(), &power, size()));
+        return out;
+    }
     Tensor prod(const Tensor &other) const {  // tensor.rs:311-322
         Tensor out(shape_.stack(other.shape_), DeviceStorage<T>(data_.ctx(), size() * other.size()));
         ctx().check(feo_outer(ctx().raw(), DT, out.ptr(), ptr(), size(), other.ptr(), other.size()));
@@ -328,6 +334,7 @@ public:
     T get(const Coordinate &c) const { return tensor_.get(c); }
     void set(const Coordinate &c, T v) { tensor_.set(c, v); }
     Tensor<T> prod(const Vector &o) const { return tensor_.prod(o.tensor_); }
+    Vector pow(T power) const { return from_tensor(tensor_.pow(power)); }  // vector.rs:94-98
     std::vector<T> to_vec() const { return tensor_.to_vec(); }
     T operator[](size_t i) const {  // Index<usize> (vector.rs:218-224): unwrap -> panic
         try { return tensor_.get(Coordinate({i})); } catch (const ShapeError &e) { throw Panic(e.what()); }
@@ -375,6 +382,7 @@ public:
     T get(const Coordinate &c) const { return tensor_.get(c); }
     void set(const Coordinate &c, T v) { tensor_.set(c, v); }
     std::vector<T> to_vec() const { return tensor_.to_vec(); }
+    Matrix pow(T power) const { return from_tensor(tensor_.pow(power)); }  // matrix.rs:106-110
     T operator[](const Coordinate &c) const {  // Index<Coordinate> (matrix.rs:230-236)
         try { return tensor_.get(c); } catch (const ShapeError &e) { throw Panic(e.what()); }
     }

@@ -125,6 +125,10 @@ FEO_API int feo_fill_uniform(feo_ctx *ctx, int dtype, void *out, size_t n, uint6
 FEO_API int feo_ewise(feo_ctx *ctx, int op, int dtype, void *out, const void *a, const void *b, size_t n);
 /* Add/Sub/Mul/Div<T> for Tensor<T> (tensor.rs:336-359, 392-402, 465-475): out[i] = a[i] op *scalar. */
 FEO_API int feo_ewise_scalar(feo_ctx *ctx, int op, int dtype, void *out, const void *a, const void *scalar_host, size_t n);
+/* Tensor::pow (tensor.rs:325-333), floats only: out[i] = a[i].powf(*power).  Exponents 2, 1, 0.5, 0, -1 use the
+ * correctly rounded multiply / sqrt / divide (what a correctly rounded powf returns); other exponents use CUDA's
+ * powf / pow, i.e. tolerance-level parity with the reference's libm (a few ulp). */
+FEO_API int feo_pow(feo_ctx *ctx, int dtype, void *out, const void *a, const void *power_host, size_t n);
 /* Broadcasting elementwise (NEW surface): out is dense row-major of `shape`;
  * a_strides / b_strides are element strides of the operands viewed at `shape`, 0 = broadcast.
  * Semantics: materialise both operands, then the reference operator. */

@@ -18,6 +18,7 @@
  * dtype codes: 0 f32, 1 f64, 2 i32, 3 i64, 4 u32.  op codes: 0 add, 1 sub, 2 mul, 3 div.
  * reduce kinds: 0 sum, 1 mean, 2 var, 3 max, 4 min.
  */
+#include <math.h>
 #include <stddef.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -308,4 +309,11 @@ int feo_oracle_fill_uniform(int dtype, void *out, size_t n, uint64_t seed, uint6
         }
     }
     return ORACLE_OK;
+}
+
+/* tensor.rs:325-333 -- result.data[i] = self.data[i].powf(power); Rust's powf is the platform libm's (glibc here). */
+int feo_oracle_pow(int dtype, void *out, const void *a, const void *power, size_t n) {
+    if (dtype == 0) { const float p = *(const float *)power; for (size_t i = 0; i < n; ++i) ((float *)out)[i] = powf(((const float *)a)[i], p); return ORACLE_OK; }
+    if (dtype == 1) { const double p = *(const double *)power; for (size_t i = 0; i < n; ++i) ((double *)out)[i] = pow(((const double *)a)[i], p); return ORACLE_OK; }
+    return ORACLE_ERR_UNSUPPORTED;
 }

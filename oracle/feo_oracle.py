@@ -283,6 +283,15 @@ def matmul_entries(A, B, rows, cols):
     return out
 
 
+def pow(a, power):
+    """tensor.rs:325-333 (Float only)."""
+    a = np.ascontiguousarray(a)
+    out = np.empty_like(a)
+    pv = np.array([power], dtype=a.dtype)
+    _chk(lib().feo_oracle_pow(_code(a.dtype), _p(out), _p(a), _p(pv), C.c_size_t(a.size)), "pow")
+    return out
+
+
 # ---- synthetic data (twin of the library's feo_fill_uniform; not part of the reference) --------------
 def fill_uniform(dtype: str, n: int, seed: int, first_index: int = 0, lo: float = -1.0, hi: float = 1.0, stride: int = 1):
     """Elements first_index, first_index + stride, ... of the counter-based stream `seed`."""

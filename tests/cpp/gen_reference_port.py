@@ -96,6 +96,10 @@ def main(out_path):
             blk.append(f"check_shape(r.shape(), {dims(c['expect_shape'])}, \"{ref}\", fails);")
             blk.append(f"check_vec(r.to_vec(), {vec(c['expect'])}, \"{ref}\", fails);")
             int_ok = True
+        elif op == "pow":
+            blk.append(make(c.get("via", "tensor"), "x", c["shape"], c["a"]))
+            blk.append(f"auto r = x.pow(T({lit(c['power'])}));")
+            blk.append(f"check_vec(r.to_vec(), {vec(c['expect'])}, \"{ref}\", fails);")
         elif op == "new_err":
             blk.append(f"expect_shape_error([&] {{ feo::Tensor<T> t({dims(c['shape'])}, {vec(c['data'])}); }}, \"{ref}\", fails);")
         elif op == "fill":

@@ -123,6 +123,14 @@ ew("tensor.rs:1267 test_mul_tensor_matrix", "mul", [2, 2], [2.0, 3.0, 4.0, 5.0],
    [2.0, 6.0, 12.0, 20.0], rhs="matrix")
 ew("tensor.rs:1282 test_div_tensor_matrix", "div", [2, 2], [2.0, 4.0, 6.0, 8.0], [1.0, 2.0, 3.0, 4.0],
    [2.0, 2.0, 2.0, 2.0], rhs="matrix")
+CASES.append(dict(ref="tensor.rs:1297 test_display_1d_tensor", op="display", shape=[3], data=[1.0, 2.0, 3.0], text="[1, 2, 3]"))
+CASES.append(dict(ref="tensor.rs:1306 test_display_2d_tensor", op="display", shape=[2, 2], data=[1.0, 2.0, 3.0, 4.0],
+                  text="[[1, 2],\n [3, 4]]"))
+CASES.append(dict(ref="tensor.rs:1315 test_display_3d_tensor", op="display", shape=[2, 2, 2],
+                  data=[1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0], text="[[[1, 2],\n  [3, 4]],\n\n [[5, 6],\n  [7, 8]]]"))
+CASES.append(dict(ref="tensor.rs:1324 test_display_4d_tensor", op="display", shape=[2, 2, 2, 2],
+                  data=[float(i) for i in range(1, 17)],
+                  text="[[[[1, 2],\n   [3, 4]],\n\n  [[5, 6],\n   [7, 8]]],\n\n\n [[[9, 10],\n   [11, 12]],\n\n  [[13, 14],\n   [15, 16]]]]"))
 CASES.append(dict(ref="tensor.rs:1335 test_pow_tensor_square", op="pow", shape=[2, 2], a=[1.0, 2.0, 3.0, 4.0],
                   power=2.0, expect=[1.0, 4.0, 9.0, 16.0]))
 CASES.append(dict(ref="tensor.rs:1345 test_pow_tensor_sqrt", op="pow", shape=[2, 2], a=[1.0, 4.0, 9.0, 16.0],

@@ -534,3 +534,28 @@ def test_matmul_tf32x3_vs_oracle(feo, oracle):
     # tiny products are refused for the explicit algorithm (AUTO runs them on the SIMT kernel)
     with pytest.raises(feo.BackendError):
         feo.Matrix(feo.shape(4, 4), np.zeros(16, np.float32)).matmul(feo.Matrix(feo.shape(4, 4), np.zeros(16, np.float32)), algo="tf32x3")
+
+
+def test_pow_and_display(feo, kat, oracle):
+    """The section-8(f) rows: pow (tensor.rs:325-333; exact on the reference's own vectors, a few ulp elsewhere) and
+    display (tensor.rs:507-551; host-side formatting)."""
+    for c in [c for c in kat if c["op"] == "pow"]:
+        for dt in FLOATS:
+            x = _mk(feo, c.get("via", "tensor"), c["shape"], c["a"], dt)
+            r = x.pow(c["power"])
+            assert type(r) is type(x) and r.shape().dims == c["shape"]
+            np.testing.assert_array_equal(r.to_numpy().reshape(-1), np.array(c["expect"], npdt(oracle, dt)), err_msg=c["ref"])
+    rng = np.random.default_rng(800)
+    for dt, rtol in (("f32", 1e-6), ("f64", 1e-14)):
+        a = rng.uniform(0.1, 4.0, 10007).astype(npdt(oracle, dt))
+        t = feo.Tensor(feo.shape(a.size), a)
+        for p in (2.0, 0.5, -1.0, 1.0, 0.0):   # correctly rounded multiply / sqrt / divide: within 1 ulp of glibc's (<1 ulp) powf
+            np.testing.assert_array_max_ulp(t.pow(p).to_numpy(), oracle.pow(a, p), maxulp=1)
+        for p in (3.0, 1.7, -2.5, 0.3333):
+            np.testing.assert_allclose(t.pow(p).to_numpy(), oracle.pow(a, p), rtol=rtol, err_msg=f"{dt} pow {p}")
+    with pytest.raises(TypeError):
+        feo.Tensor(feo.shape(2), np.array([1, 2], np.int32)).pow(2)
+    for c in [c for c in kat if c["op"] == "display"]:
+        assert feo.Tensor(feo.Shape(c["shape"]), c["data"]).display() == c["text"], c["ref"]
+    assert feo.Tensor(feo.shape(3), np.array([1.5, -0.25, 1e21], np.float64)).display() == "[1.5, -0.25, 1000000000000000000000]"
+    assert feo.Tensor(feo.shape(2), np.array([7, -3], np.int32)).display() == "[7, -3]"

@@ -173,3 +173,14 @@ def test_oracle_matches_numpy_on_exact_data(oracle, dt):
     np.testing.assert_array_equal(oracle.matmul(A, B), A @ B)
     np.testing.assert_array_equal(oracle.matvec(A, B[:, 0].copy()), A @ B[:, 0])
     np.testing.assert_array_equal(oracle.vecmat(A[:, 0].copy(), A), A[:, 0] @ A)
+
+
+def test_pow_kats(oracle, kat):
+    """tensor.rs:1335-1365, matrix.rs:645, vector.rs:596 -- exact on these inputs with a correctly rounded libm."""
+    n = 0
+    for c in _cases(kat, "pow"):
+        for dt in FLOATS:
+            a = np.array(c["a"], dtype=_np(oracle, dt))
+            np.testing.assert_array_equal(oracle.pow(a, c["power"]), np.array(c["expect"], dtype=a.dtype), err_msg=c["ref"])
+            n += 1
+    assert n == 10
