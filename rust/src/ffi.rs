@@ -1,0 +1,61 @@
+//! bindgen-style declarations of include/feotensor_b200.h (one per FEO_API symbol the crate uses).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct feo_ctx {
+    _private: [u8; 0],
+}
+
+pub const FEO_OK: c_int = 0;
+pub const FEO_ERR_SHAPE: c_int = 1;
+pub const FEO_ERR_CUDA: c_int = 2;
+pub const FEO_ERR_UNSUPPORTED: c_int = 3;
+
+pub const FEO_F32: c_int = 0;
+pub const FEO_F64: c_int = 1;
+pub const FEO_I32: c_int = 2;
+pub const FEO_I64: c_int = 3;
+pub const FEO_U32: c_int = 4;
+
+pub const FEO_ADD: c_int = 0;
+pub const FEO_SUB: c_int = 1;
+pub const FEO_MUL: c_int = 2;
+pub const FEO_DIV: c_int = 3;
+
+pub const FEO_SUM: c_int = 0;
+pub const FEO_MEAN: c_int = 1;
+pub const FEO_VAR: c_int = 2;
+pub const FEO_MAX: c_int = 3;
+pub const FEO_MIN: c_int = 4;
+
+pub const FEO_MATMUL_AUTO: c_int = 0;
+pub const FEO_MATMUL_SIMT: c_int = 1;
+pub const FEO_MATMUL_TF32X3: c_int = 2;
+
+extern "C" {
+    pub fn feo_init(device: c_int, ctx: *mut *mut feo_ctx) -> c_int;
+    pub fn feo_shutdown(ctx: *mut feo_ctx) -> c_int;
+    pub fn feo_last_error(ctx: *mut feo_ctx) -> *const c_char;
+    pub fn feo_sync(ctx: *mut feo_ctx) -> c_int;
+    pub fn feo_malloc(ctx: *mut feo_ctx, bytes: usize, dptr: *mut *mut c_void) -> c_int;
+    pub fn feo_free(ctx: *mut feo_ctx, dptr: *mut c_void) -> c_int;
+    pub fn feo_upload(ctx: *mut feo_ctx, dst_dev: *mut c_void, src_host: *const c_void, bytes: usize) -> c_int;
+    pub fn feo_download(ctx: *mut feo_ctx, dst_host: *mut c_void, src_dev: *const c_void, bytes: usize) -> c_int;
+    pub fn feo_flatten(coord_rank: c_int, coord: *const usize, rank: c_int, shape: *const usize, index: *mut usize, detail: *mut c_int) -> c_int;
+    pub fn feo_reduce_shape(rank: c_int, shape: *const usize, naxes: c_int, axes: *const usize, out_rank: *mut c_int, out_shape: *mut usize) -> c_int;
+    pub fn feo_fill(ctx: *mut feo_ctx, dtype: c_int, out: *mut c_void, value: *const c_void, n: usize) -> c_int;
+    pub fn feo_eye(ctx: *mut feo_ctx, dtype: c_int, out: *mut c_void, rows: usize, cols: usize) -> c_int;
+    pub fn feo_ewise(ctx: *mut feo_ctx, op: c_int, dtype: c_int, out: *mut c_void, a: *const c_void, b: *const c_void, n: usize) -> c_int;
+    pub fn feo_ewise_scalar(ctx: *mut feo_ctx, op: c_int, dtype: c_int, out: *mut c_void, a: *const c_void, scalar_host: *const c_void, n: usize) -> c_int;
+    pub fn feo_ewise_broadcast(ctx: *mut feo_ctx, op: c_int, dtype: c_int, out: *mut c_void, a: *const c_void, b: *const c_void, rank: c_int,
+                               shape: *const usize, a_strides: *const usize, b_strides: *const usize) -> c_int;
+    pub fn feo_pow(ctx: *mut feo_ctx, dtype: c_int, out: *mut c_void, a: *const c_void, power_host: *const c_void, n: usize) -> c_int;
+    pub fn feo_reduce(ctx: *mut feo_ctx, kind: c_int, dtype: c_int, out: *mut c_void, input: *const c_void, rank: c_int, shape: *const usize,
+                      naxes: c_int, axes: *const usize) -> c_int;
+    pub fn feo_outer(ctx: *mut feo_ctx, dtype: c_int, out: *mut c_void, a: *const c_void, na: usize, b: *const c_void, nb: usize) -> c_int;
+    pub fn feo_dot(ctx: *mut feo_ctx, dtype: c_int, out: *mut c_void, a: *const c_void, b: *const c_void, n: usize) -> c_int;
+    pub fn feo_matvec(ctx: *mut feo_ctx, dtype: c_int, out: *mut c_void, a: *const c_void, v: *const c_void, m: usize, k: usize) -> c_int;
+    pub fn feo_vecmat(ctx: *mut feo_ctx, dtype: c_int, out: *mut c_void, v: *const c_void, a: *const c_void, k: usize, n: usize) -> c_int;
+    pub fn feo_matmul(ctx: *mut feo_ctx, algo: c_int, dtype: c_int, c: *mut c_void, a: *const c_void, b: *const c_void, m: usize, k: usize, n: usize) -> c_int;
+}
