@@ -93,12 +93,16 @@ struct BcastParams {
     // block geometry
     int tx, ty;  // threads along inner vectors / along q tiles (tx * ty == kThreads)
     long long i_blocks, q_blocks, p_tiles;
+    int keep_operands;  // 1: load operands with the L2 evict_last policy
 };
 
-template <typename T, int VB> __device__ __forceinline__ AVec<T, VecW<T, VB>::value> load_operand(const T *p, int inner) {
+template <typename T, int VB> __device__ __forceinline__ AVec<T, VecW<T, VB>::value> load_operand(const T *p, int inner, unsigned long long pol = 0) {
     constexpr int VN = VecW<T, VB>::value;
     using V = AVec<T, VN>;
-    if (inner) return ld_keep(reinterpret_cast<const V *>(p));
+    if (inner) {
+        if constexpr (VB == 16) { if (pol) return ld_keep_last(reinterpret_cast<const V *>(p), pol); }
+        return ld_keep(reinterpret_cast<const V *>(p));
+    }
     V r;
     const T s = __ldg(p);
 #pragma unroll
@@ -116,6 +120,8 @@ __global__ void __launch_bounds__(kThreads) bcast_tile_kernel(T *__restrict__ ou
                                                               int *flag) {
     constexpr int VN = VecW<T, VB>::value;
     using V = AVec<T, VN>;
+    // programmatic dependent launch: let the next (independent) launch start filling SMs as this grid's tail drains
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     long long blk = blockIdx.x;
     const long long bi = blk % P.i_blocks; blk /= P.i_blocks;
     const long long bp = blk % P.p_tiles;  blk /= P.p_tiles;
@@ -134,6 +140,9 @@ __global__ void __launch_bounds__(kThreads) bcast_tile_kernel(T *__restrict__ ou
     const long long q0 = (bq * P.ty + ty) * QT;
     if (q0 >= P.nq) return;
     oa += iv * VN * P.a_inner; ob += iv * VN * P.b_inner; oo += iv * VN;
+    // operands are re-read (by other CTAs now, by the next slab launch later) while the output streams through L2 once:
+    // operands evict_last, output evict_first
+    const unsigned long long pol = P.keep_operands ? l2_policy_evict_last() : 0ull;
 
     V va[A_QINV ? PT : PT * QT], vb[B_PINV ? QT : PT * QT];
 #pragma unroll
@@ -142,7 +151,7 @@ __global__ void __launch_bounds__(kThreads) bcast_tile_kernel(T *__restrict__ ou
 #pragma unroll
             for (int q = 0; q < (A_QINV ? 1 : QT); ++q)
                 if (A_QINV || q0 + q < P.nq)
-                    va[A_QINV ? p : p * QT + q] = load_operand<T, VB>(a + oa + (p0 + p) * P.sa_p + (q0 + q) * P.sa_q, P.a_inner);
+                    va[A_QINV ? p : p * QT + q] = load_operand<T, VB>(a + oa + (p0 + p) * P.sa_p + (q0 + q) * P.sa_q, P.a_inner, pol);
         }
     }
 #pragma unroll
@@ -151,7 +160,7 @@ __global__ void __launch_bounds__(kThreads) bcast_tile_kernel(T *__restrict__ ou
 #pragma unroll
             for (int p = 0; p < (B_PINV ? 1 : PT); ++p)
                 if (B_PINV || p0 + p < P.np)
-                    vb[B_PINV ? q : p * QT + q] = load_operand<T, VB>(b + ob + (p0 + p) * P.sb_p + (q0 + q) * P.sb_q, P.b_inner);
+                    vb[B_PINV ? q : p * QT + q] = load_operand<T, VB>(b + ob + (p0 + p) * P.sb_p + (q0 + q) * P.sb_q, P.b_inner, pol);
         }
     }
 #pragma unroll
@@ -317,8 +326,22 @@ int launch_tile(feo_ctx *ctx, T *out, const T *a, const T *b, BcastParams &P) {
     long long blocks = P.i_blocks * P.q_blocks * P.p_tiles;
     for (int d = 0; d < P.nrest; ++d) blocks *= P.rest_ext[d];
     if (blocks > 0x7fffffffLL) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "broadcast grid too large");
-    bcast_tile_kernel<T, OP, VB, PT, QT, A_QINV, B_PINV><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, a, b, P, ctx->arith_flag);
-    FEO_LAUNCH_CHECK(ctx);
+    // Back-to-back launches whose operands do not overlap (e.g. the 1 GiB slabs of one big broadcast) carry the
+    // programmatic-stream-serialization attribute: their CTAs start as the previous grid's tail drains.
+    const bool pdl = feo_pdl_admit(ctx);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    int *flag = ctx->arith_flag;
+    const T *ca = a, *cb = b;
+    FEO_CUDA(ctx, cudaLaunchKernelEx(&cfg, bcast_tile_kernel<T, OP, VB, PT, QT, A_QINV, B_PINV>, out, ca, cb, P, flag));
+    ctx->launches++;
     return FEO_OK;
 }
 
@@ -404,6 +427,7 @@ int broadcast_vec(feo_ctx *ctx, T *out, const T *a, const T *b, const Collapsed 
     P.tx = tx;
     P.ty = kThreads / tx;
     P.i_blocks = (P.ni_vec + tx - 1) / tx;
+    P.keep_operands = (ctx->knobs[FEO_KNOB_BCAST_L2KEEP] != 1);
 
     const bool both = pd >= 0 && qd >= 0;
     if (both && knob != 3) {
@@ -455,6 +479,14 @@ int broadcast_typed(feo_ctx *ctx, T *out, const T *a, const T *b, int rank, cons
     // same-shape after collapsing: the flat kernel is the right tool
     if (c.rank == 1 && c.sa[0] == 1 && c.sb[0] == 1 && knob != 4)
         return launch_flat<T, OP, false>(ctx, out, a, b, (T)0, (size_t)c.ext[0]);
+    {   // byte ranges of this launch for the overlap hazard check (feo_pdl_admit)
+        long long no = 1, ea = 0, eb = 0;
+        for (int d = 0; d < c.rank; ++d) { no *= c.ext[d]; ea += (c.ext[d] - 1) * c.sa[d]; eb += (c.ext[d] - 1) * c.sb[d]; }
+        ctx->pending.out = {(uintptr_t)out, (uintptr_t)(out + no)};
+        ctx->pending.in[0] = {(uintptr_t)a, (uintptr_t)(a + ea + 1)};
+        ctx->pending.in[1] = {(uintptr_t)b, (uintptr_t)(b + eb + 1)};
+        ctx->pending_valid = true;
+    }
     if (knob != 4) {
         int rc = -1;
         rc = broadcast_vec<T, OP, 16>(ctx, out, a, b, c, knob);

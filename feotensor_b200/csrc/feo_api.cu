@@ -16,6 +16,25 @@ int feo_fail(feo_ctx *ctx, int status, const char *fmt, ...) {
     return status;
 }
 
+bool feo_pdl_admit(feo_ctx *ctx) {
+    if (!ctx->pending_valid || ctx->knobs[FEO_KNOB_PDL] == 1) { ctx->window.clear(); return false; }
+    ctx->pending_valid = false;
+    const feo_launch_rec &r = ctx->pending;
+    auto hit = [](const feo_range &x, const feo_range &y) { return x.lo < y.hi && y.lo < x.hi; };
+    // A kernel may still have CTAs running when the kernel 2+ launches later starts, so the check covers the whole window,
+    // and a full window forces one fully ordered launch.
+    bool independent = ctx->window.size() < 16;
+    for (size_t i = 0; independent && i < ctx->window.size(); ++i) {
+        const feo_launch_rec &w = ctx->window[i];
+        if (hit(r.out, w.out)) independent = false;
+        for (int k = 0; k < 2 && independent; ++k)
+            if (hit(r.out, w.in[k]) || hit(r.in[k], w.out)) independent = false;
+    }
+    if (!independent) ctx->window.clear();
+    ctx->window.push_back(r);
+    return independent;
+}
+
 int feo_workspace(feo_ctx *ctx, size_t bytes, void **ptr) {
     if (bytes > ctx->workspace_bytes) {
         if (ctx->workspace) FEO_CUDA(ctx, cudaFreeAsync(ctx->workspace, ctx->stream));
@@ -103,7 +122,7 @@ int feo_malloc(feo_ctx *ctx, size_t bytes, void **dptr) {
     return FEO_OK;
 }
 int feo_free(feo_ctx *ctx, void *dptr) {
-    if (dptr) FEO_CUDA(ctx, cudaFreeAsync(dptr, ctx->stream));
+    if (dptr) FEO_CUDA(ctx, cudaFreeAsync(dptr, ctx->stream));  // stream-ordered: takes effect after every earlier kernel
     return FEO_OK;
 }
 int feo_host_alloc(feo_ctx *ctx, size_t bytes, void **hptr) {

@@ -7,6 +7,7 @@
 
 #include <limits>
 #include <string>
+#include <vector>
 #include <type_traits>
 
 #include "../../include/feotensor_b200.h"
@@ -18,8 +19,14 @@ enum feo_knob {
     FEO_KNOB_REDUCE_BLOCKS_PER_SM = 2,  // target resident blocks per SM used by the split planner (0 = auto)
     FEO_KNOB_MATMUL_TF32_KC = 3,  // k-blocks (of 32) per TMEM accumulation chunk in the 3xTF32 matmul (0 = default 2)
     FEO_KNOB_BCAST_LCHUNK = 4,  // rows of the loop dimension per thread in the hold+stream broadcast kernel (0 = auto)
+    FEO_KNOB_PDL = 5,           // programmatic dependent launch of independent back-to-back broadcast kernels: 0 = on, 1 = off
+    FEO_KNOB_BCAST_L2KEEP = 6,  // L2 evict_last policy on broadcast operands: 0 = on, 1 = off
     FEO_KNOB_COUNT = 8
 };
+
+// Address ranges of a launch, for the hazard check that lets independent back-to-back kernels overlap their tails.
+struct feo_range { uintptr_t lo = 0, hi = 0; };
+struct feo_launch_rec { feo_range out, in[2]; };
 
 struct feo_ctx {
     int device = 0;
@@ -31,10 +38,16 @@ struct feo_ctx {
     int *arith_flag = nullptr;          // device int, sticky
     uint64_t launches = 0;
     int knobs[FEO_KNOB_COUNT] = {0};
+    std::vector<feo_launch_rec> window;  // launches since the last fully serialising operation (see feo_pdl_admit)
+    feo_launch_rec pending;              // ranges of the launch being prepared
+    bool pending_valid = false;
     std::string last_error;
 };
 
 int feo_fail(feo_ctx *ctx, int status, const char *fmt, ...);
+// True if the launch described by ctx->pending may start before the kernels in the window have finished (no RAW / WAR /
+// WAW overlap with any of them, window not full); records it.  False: launch normally (full stream order).
+bool feo_pdl_admit(feo_ctx *ctx);
 int feo_workspace(feo_ctx *ctx, size_t bytes, void **ptr);
 
 #define FEO_CUDA(ctx, expr)                                                                       \
@@ -45,9 +58,12 @@ int feo_workspace(feo_ctx *ctx, size_t bytes, void **ptr);
                             __FILE__, __LINE__);                                                  \
     } while (0)
 
+// A normally launched kernel starts after everything before it in the stream has finished: the overlap window closes.
 #define FEO_LAUNCH_CHECK(ctx)          \
     do {                               \
         (ctx)->launches++;             \
+        (ctx)->window.clear();         \
+        (ctx)->pending_valid = false;  \
         FEO_CUDA(ctx, cudaGetLastError()); \
     } while (0)
 
@@ -146,6 +162,21 @@ template <typename V> __device__ __forceinline__ V ld_keep(const V *p) {
         uint32_t t = __ldg(reinterpret_cast<const uint32_t *>(p));
         __builtin_memcpy(&r, &t, 4);
     }
+    return r;
+}
+// Reused operand that should survive a large write stream in L2 (e.g. the broadcast operand re-read by every slab
+// launch): 128-bit read-only load with an L2 evict_last cache policy.
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <typename V> __device__ __forceinline__ V ld_keep_last(const V *p, unsigned long long pol) {
+    static_assert(sizeof(V) == 16, "128-bit only");
+    V r;
+    uint4 t;
+    asm("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p), "l"(pol));
+    __builtin_memcpy(&r, &t, 16);
     return r;
 }
 // Streaming store (evict-first): results are written once and not re-read by the kernel.

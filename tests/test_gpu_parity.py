@@ -559,3 +559,46 @@ def test_pow_and_display(feo, kat, oracle):
         assert feo.Tensor(feo.Shape(c["shape"]), c["data"]).display() == c["text"], c["ref"]
     assert feo.Tensor(feo.shape(3), np.array([1.5, -0.25, 1e21], np.float64)).display() == "[1.5, -0.25, 1000000000000000000000]"
     assert feo.Tensor(feo.shape(2), np.array([7, -3], np.int32)).display() == "[7, -3]"
+
+
+def test_overlapped_launches_respect_hazards(feo, oracle):
+    """Independent back-to-back broadcast launches overlap (programmatic dependent launch); launches that read or
+    overwrite what an in-flight launch produces must stay ordered.  Integer data: any mis-ordering changes the bits."""
+    import feotensor_b200._lib as L
+    ctx = feo.Context.default()
+    lib = ctx.lib
+    rng = np.random.default_rng(900)
+    R, Q, D = 16, 96, 256
+    a = rand(oracle, rng, "i32", (R, 1, D))
+    b = rand(oracle, rng, "i32", (1, Q, D))
+    ta, tb = feo.Tensor(feo.shape(R, 1, D), a), feo.Tensor(feo.shape(1, Q, D), b)
+    ab = oracle.ewise_broadcast("add", a, b)
+    for knob in (0, 1):  # PDL on / off give the same bits
+        ctx.tune(L.KNOB_PDL, knob)
+        # (1) RAW chain: x_{k+1} = x_k[R,Q,D] + b (b broadcast along dim 0); every launch reads the previous output
+        x = ta.broadcast("add", tb)
+        want = ab.copy()
+        for _ in range(40):
+            x = x.broadcast("add", tb)
+            want = oracle.ewise_broadcast("add", want, b)
+        np.testing.assert_array_equal(x.to_numpy(), want)
+        # (2) 64 independent slab launches into one buffer, then overwrite every slab (WAW) and read it back
+        out = feo.Tensor.zeros(feo.shape(64 * R, Q, D), "i32")
+        slab = R * Q * D
+        shape, sa, sb = L.sizes([R, Q, D]), L.sizes([D, 0, 1]), L.sizes([0, D, 1])
+        for op in (L.ADD, L.MUL, L.SUB):
+            for s in range(64):
+                ctx.check(lib.feo_ewise_broadcast(ctx.handle, op, L.I32, C.c_void_p(out.data.ptr + 4 * s * slab), C.c_void_p(ta.data.ptr),
+                                                  C.c_void_p(tb.data.ptr), 3, shape, sa, sb))
+        got = out.to_numpy().reshape(64, R, Q, D)
+        want_sub = oracle.ewise_broadcast("sub", a, b)
+        for s in (0, 1, 31, 63):
+            np.testing.assert_array_equal(got[s], want_sub)
+        # (3) WAR: a launch overwrites the operand an earlier, possibly still running launch reads
+        src = feo.Tensor(feo.shape(R, 1, D), a)
+        o1 = src.broadcast("add", tb)                       # reads src
+        ctx.check(lib.feo_ewise_broadcast(ctx.handle, L.MUL, L.I32, C.c_void_p(src.data.ptr), C.c_void_p(ta.data.ptr),
+                                          C.c_void_p(ta.data.ptr), 3, L.sizes([R, 1, D]), L.sizes([D, 0, 1]), L.sizes([D, 0, 1])))  # overwrites src
+        np.testing.assert_array_equal(o1.to_numpy(), ab)
+        np.testing.assert_array_equal(src.to_numpy(), oracle.ewise("mul", a, a))
+    ctx.tune(L.KNOB_PDL, 0)

@@ -35,6 +35,9 @@ def main():
     ap.add_argument("--bpsm", type=int, default=0)
     ap.add_argument("--lchunk", type=int, default=0)
     ap.add_argument("--kc", type=int, default=0)
+    ap.add_argument("--pdl", type=int, default=0, help="1 = disable programmatic dependent launch")
+    ap.add_argument("--slabs", type=int, default=1)
+    ap.add_argument("--l2keep", type=int, default=0, help="1 = disable the evict_last policy on broadcast operands")
     args = ap.parse_args()
 
     import torch
@@ -51,6 +54,8 @@ def main():
     ctx.tune(L.KNOB_REDUCE_BLOCKS_PER_SM, args.bpsm)
     ctx.tune(L.KNOB_BCAST_LCHUNK, args.lchunk)
     ctx.tune(L.KNOB_MATMUL_TF32_KC, args.kc)
+    ctx.tune(L.KNOB_PDL, args.pdl)
+    ctx.tune(L.KNOB_BCAST_L2KEEP, args.l2keep)
     lib, h, vp = ctx.lib, ctx.handle, C.c_void_p
     dt = L.code_of(args.dtype)
     es = L.np_dtype(args.dtype).itemsize
@@ -96,11 +101,15 @@ def main():
                   f"reduce {kind} {shape} axes {axes} {args.dtype}", nbytes=es * (nin + nout))
     elif args.case == "bcast":
         D, R = 4096, args.rows
-        a, b, o = dev(R * D), dev(D * D), dev(R * D * D)
-        fill(a, R * D, 2); fill(b, D * D, 3)
-        timed(lambda: ctx.check(lib.feo_ewise_broadcast(h, L.MUL, dt, vp(o.data_ptr()), vp(a.data_ptr()), vp(b.data_ptr()), 3,
-                                                        L.sizes([R, D, D]), L.sizes([D, 0, 1]), L.sizes([0, D, 1]))),
-              f"bcast mul [{R},1,{D}]*[1,{D},{D}] tile={args.tile} lchunk={args.lchunk}", nbytes=es * (R * D + D * D + R * D * D))
+        S = args.slabs
+        a, b, o = dev(S * R * D), dev(D * D), dev(S * R * D * D)
+        fill(a, S * R * D, 2); fill(b, D * D, 3)
+
+        def slabs():
+            for s in range(S):
+                ctx.check(lib.feo_ewise_broadcast(h, L.MUL, dt, vp(o.data_ptr() + es * s * R * D * D), vp(a.data_ptr() + es * s * R * D),
+                                                  vp(b.data_ptr()), 3, L.sizes([R, D, D]), L.sizes([D, 0, 1]), L.sizes([0, D, 1])))
+        timed(slabs, f"bcast mul {S} x [{R},1,{D}]*[1,{D},{D}] tile={args.tile} pdl_off={args.pdl} l2keep_off={args.l2keep}", nbytes=S * es * (R * D + D * D + R * D * D))
     elif args.case == "outer":
         n = args.n
         u, v, o = dev(n), dev(n), dev(n * n)
