@@ -79,6 +79,12 @@ int feo_init(int device, feo_ctx **out) {
         delete ctx;
         return FEO_ERR_CUDA;
     }
+    ctx->counters_len = size_t(1) << 20;
+    if (cudaMalloc(&ctx->counters, ctx->counters_len * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(ctx->counters, 0, ctx->counters_len * sizeof(unsigned int)) != cudaSuccess) {
+        ctx->counters = nullptr;
+        ctx->counters_len = 0;  // fall back to the two-launch combine
+    }
     *out = ctx;
     return FEO_OK;
 }
@@ -89,6 +95,7 @@ int feo_shutdown(feo_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->workspace) cudaFree(ctx->workspace);
     if (ctx->arith_flag) cudaFree(ctx->arith_flag);
+    if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return FEO_OK;

@@ -21,6 +21,7 @@ enum feo_knob {
     FEO_KNOB_BCAST_LCHUNK = 4,  // rows of the loop dimension per thread in the hold+stream broadcast kernel (0 = auto)
     FEO_KNOB_PDL = 5,           // programmatic dependent launch of independent back-to-back broadcast kernels: 0 = on, 1 = off
     FEO_KNOB_BCAST_L2KEEP = 6,  // L2 evict_last policy on broadcast operands: 0 = on, 1 = off
+    FEO_KNOB_REDUCE_FUSE = 7,   // split reductions: last-arriving CTA combines the partials in the same launch: 0 = auto (small inputs), 1 = off, 2 = always
     FEO_KNOB_COUNT = 8
 };
 
@@ -36,6 +37,8 @@ struct feo_ctx {
     void *workspace = nullptr;          // scratch for two-stage reductions
     size_t workspace_bytes = 0;
     int *arith_flag = nullptr;          // device int, sticky
+    unsigned int *counters = nullptr;   // zeroed arrival counters for the fused reduction combine
+    size_t counters_len = 0;
     uint64_t launches = 0;
     int knobs[FEO_KNOB_COUNT] = {0};
     std::vector<feo_launch_rec> window;  // launches since the last fully serialising operation (see feo_pdl_admit)
@@ -122,7 +125,8 @@ template <typename T> struct VecN { static constexpr int value = 16 / sizeof(T);
 // sm_100 adds 256-bit global accesses (LDG.E.256 / STG.E.256): one 32-byte sector per thread per instruction.
 template <typename T, int BYTES> struct VecW { static constexpr int value = BYTES / (int)sizeof(T); };
 
-// Streaming (read-once) load: bypass L1 allocation.
+// Streaming (read-once) load: bypass L1 allocation.  (Not `volatile`: the compiler may hoist the next batch's loads
+// above the current batch's arithmetic; batches are combined as trees so the loads of one batch stay grouped.)
 template <typename V> __device__ __forceinline__ V ld_stream(const V *p) {
     static_assert(sizeof(V) == 32 || sizeof(V) == 16 || sizeof(V) == 8 || sizeof(V) == 4, "vector size");
     V r;

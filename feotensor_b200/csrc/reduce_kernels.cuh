@@ -32,9 +32,23 @@ template <typename T> struct Acc<T, K_SUM> {
     __device__ __forceinline__ void init(T) { v = (T)0; }
     __device__ __forceinline__ void push(T x) { v = w_add(v, x); }
     __device__ __forceinline__ void merge(const Acc &o) { v = w_add(v, o.v); }
+    // Batches are combined as a balanced tree: short dependency chains, and every load of the batch is needed by the
+    // first level, so the scheduler keeps the loads grouped ahead of the arithmetic (a serial chain made ptxas sink each
+    // load next to its use: one load in flight per thread, -20 % on the rows kernel).
     template <int N> __device__ __forceinline__ void push_batch(const T (&x)[N]) {
+        if constexpr ((N & (N - 1)) == 0 && N >= 2) {
+            T t[N / 2];
 #pragma unroll
-        for (int i = 0; i < N; ++i) push(x[i]);
+            for (int i = 0; i < N / 2; ++i) t[i] = w_add(x[i], x[i + N / 2]);
+#pragma unroll
+            for (int w = N / 4; w >= 1; w /= 2)
+#pragma unroll
+                for (int i = 0; i < w; ++i) t[i] = w_add(t[i], t[i + w]);
+            push(t[0]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) push(x[i]);
+        }
     }
 };
 template <typename T> struct Acc<T, K_SQDEV> {  // sum of (x - mean)^2 for a given mean (integer var, tensor.rs:196-198)
@@ -52,9 +66,24 @@ template <typename T> struct Acc<T, K_MAX> {
     __device__ __forceinline__ void init(T) { v = std::numeric_limits<T>::lowest(); }
     __device__ __forceinline__ void push(T x) { v = (x > v) ? x : v; }  // strict compare, tensor.rs:248
     __device__ __forceinline__ void merge(const Acc &o) { push(o.v); }
+    static __device__ __forceinline__ T pick(T a, T b) { return (b > a) ? b : a; }
+    // Batches are combined as a balanced tree: short dependency chains, and every load of the batch is needed by the
+    // first level, so the scheduler keeps the loads grouped ahead of the arithmetic (a serial chain made ptxas sink each
+    // load next to its use: one load in flight per thread, -20 % on the rows kernel).
     template <int N> __device__ __forceinline__ void push_batch(const T (&x)[N]) {
+        if constexpr ((N & (N - 1)) == 0 && N >= 2) {
+            T t[N / 2];
 #pragma unroll
-        for (int i = 0; i < N; ++i) push(x[i]);
+            for (int i = 0; i < N / 2; ++i) t[i] = pick(x[i], x[i + N / 2]);
+#pragma unroll
+            for (int w = N / 4; w >= 1; w /= 2)
+#pragma unroll
+                for (int i = 0; i < w; ++i) t[i] = pick(t[i], t[i + w]);
+            push(t[0]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) push(x[i]);
+        }
     }
 };
 template <typename T> struct Acc<T, K_MIN> {
@@ -62,9 +91,24 @@ template <typename T> struct Acc<T, K_MIN> {
     __device__ __forceinline__ void init(T) { v = std::numeric_limits<T>::max(); }
     __device__ __forceinline__ void push(T x) { v = (x < v) ? x : v; }  // tensor.rs:300
     __device__ __forceinline__ void merge(const Acc &o) { push(o.v); }
+    static __device__ __forceinline__ T pick(T a, T b) { return (b < a) ? b : a; }
+    // Batches are combined as a balanced tree: short dependency chains, and every load of the batch is needed by the
+    // first level, so the scheduler keeps the loads grouped ahead of the arithmetic (a serial chain made ptxas sink each
+    // load next to its use: one load in flight per thread, -20 % on the rows kernel).
     template <int N> __device__ __forceinline__ void push_batch(const T (&x)[N]) {
+        if constexpr ((N & (N - 1)) == 0 && N >= 2) {
+            T t[N / 2];
 #pragma unroll
-        for (int i = 0; i < N; ++i) push(x[i]);
+            for (int i = 0; i < N / 2; ++i) t[i] = pick(x[i], x[i + N / 2]);
+#pragma unroll
+            for (int w = N / 4; w >= 1; w /= 2)
+#pragma unroll
+                for (int i = 0; i < w; ++i) t[i] = pick(t[i], t[i + w]);
+            push(t[0]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) push(x[i]);
+        }
     }
 };
 // Welford / Chan: (count, mean, M2).  Batches are combined two-pass in registers and merged with one
@@ -137,11 +181,75 @@ __device__ __forceinline__ void finalize(const Acc<T, KIND> &acc, T *out, long l
         out[o] = v;
     }
 }
+// L2-coherent read of a partial accumulator written by another CTA of the same launch.
+template <typename T, int KIND> __device__ __forceinline__ Acc<T, KIND> load_partial(const void *partial, long long idx) {
+    static_assert(sizeof(Acc<T, KIND>) % 4 == 0, "accumulators are made of 32-bit words");
+    Acc<T, KIND> r;
+    const unsigned int *src = reinterpret_cast<const unsigned int *>(reinterpret_cast<const Acc<T, KIND> *>(partial) + idx);
+    unsigned int w[sizeof(Acc<T, KIND>) / 4];
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(Acc<T, KIND>) / 4); ++i) w[i] = __ldcg(src + i);
+    __builtin_memcpy(&r, w, sizeof r);
+    return r;
+}
+
+// The last arriver's merge, out of line so the rarely taken path does not inflate the streaming kernels' registers.
+template <typename T, int KIND>
+__device__ __noinline__ void combine_thread(T *out, const void *partial, long long o, long long nout, long long S, int fin, T divisor,
+                                            int *flag, unsigned int *counters) {
+    __threadfence();
+    Acc<T, KIND> m = load_partial<T, KIND>(partial, o);
+    constexpr int B = 8;  // partials fetched per round: independent loads in flight, merged in split order
+    for (long long k = 1; k < S; k += B) {
+        Acc<T, KIND> buf[B];
+#pragma unroll
+        for (int i = 0; i < B; ++i)
+            if (k + i < S) buf[i] = load_partial<T, KIND>(partial, (k + i) * nout + o);
+#pragma unroll
+        for (int i = 0; i < B; ++i)
+            if (k + i < S) m.merge(buf[i]);
+    }
+    finalize(m, out, o, nout, fin, divisor, flag);
+    counters[o] = 0;  // ready for the next launch on this stream
+}
+
+// Result of one (output, split) pair, thread level (cols / micro kernels).  S == 1: final value.  S > 1: the accumulator
+// goes to the workspace; with `counters` the LAST of the S writers of this output merges all S partials in split order
+// (so the result does not depend on who is last) and finalises -- one launch instead of two, no atomics on data.
 template <typename T, int KIND>
 __device__ __forceinline__ void emit(const Acc<T, KIND> &acc, T *out, void *partial, long long o, long long s, long long nout,
-                                     long long S, int fin, T divisor, int *flag) {
-    if (S > 1) reinterpret_cast<Acc<T, KIND> *>(partial)[s * nout + o] = acc;
-    else finalize(acc, out, o, nout, fin, divisor, flag);
+                                     long long S, int fin, T divisor, int *flag, unsigned int *counters) {
+    if (S <= 1) { finalize(acc, out, o, nout, fin, divisor, flag); return; }
+    reinterpret_cast<Acc<T, KIND> *>(partial)[s * nout + o] = acc;
+    if (!counters) return;  // two-stage mode: reduce_stage2_kernel combines
+    __threadfence();
+    const unsigned int ticket = atomicAdd(&counters[o], 1u);
+    if (ticket != (unsigned int)(S - 1)) return;
+    combine_thread<T, KIND>(out, partial, o, nout, S, fin, divisor, flag, counters);
+}
+
+// Warp-level merge of the S partials of output o (same order as reduce_stage2_kernel<WARP>): every lane of the calling
+// warp takes a contiguous run of splits, then the fixed shuffle tree.
+template <typename T, int KIND>
+__device__ __noinline__ void warp_combine(T *out, const void *partial, long long o, long long nout, long long S, int fin, T divisor,
+                                             int *flag, unsigned int *counters, int lane) {
+    Acc<T, KIND> m;
+    m.init((T)0);
+    if constexpr (KIND == K_SQDEV) m.m = load_partial<T, KIND>(partial, o).m;
+    const long long per = (S + 31) / 32;
+    const long long lo = lane * per, hi = (lo + per < S) ? lo + per : S;
+    constexpr int B = 4;
+    for (long long k = lo; k < hi; k += B) {
+        Acc<T, KIND> buf[B];
+#pragma unroll
+        for (int i = 0; i < B; ++i)
+            if (k + i < hi) buf[i] = load_partial<T, KIND>(partial, (k + i) * nout + o);
+#pragma unroll
+        for (int i = 0; i < B; ++i)
+            if (k + i < hi) m.merge(buf[i]);
+    }
+    warp_merge(m);
+    if (lane == 0) { finalize(m, out, o, nout, fin, divisor, flag); counters[o] = 0; }
 }
 
 struct Geom {
@@ -153,6 +261,7 @@ struct Geom {
     int fin;
     int lanes;                 // rows kernel: 32 (warp per output) or 256 (block per output)
     int lx;                    // rows kernel: lanes along the row (power of two <= lanes); lanes / lx rows at a time
+    unsigned int *counters;    // per-output arrival counters for the fused combine (nullptr: two-stage)
 };
 
 // ---- cols: in[k1][r1][k2] -> out[k1][k2], threads along k2 ---------------------------------------------
@@ -209,7 +318,7 @@ __global__ void __launch_bounds__(kThreads) reduce_cols_kernel(T *__restrict__ o
         for (int k = 0; k < W; ++k) acc[k].push(v.v[k]);
     }
 #pragma unroll
-    for (int k = 0; k < W; ++k) emit(acc[k], out, partial, o0 + k, s, G.nout, G.S, G.fin, divisor, flag);
+    for (int k = 0; k < W; ++k) emit(acc[k], out, partial, o0 + k, s, G.nout, G.S, G.fin, divisor, flag, G.counters);
 }
 
 // ---- micro: in[k1][r1][k2][r2] with 2 <= r2 <= 32 ----------------------------------------------------------
@@ -269,7 +378,7 @@ __global__ void __launch_bounds__(kThreads) reduce_micro_kernel(T *__restrict__ 
                     Acc<T, KIND> a1;
                     a1.init(aux_val<KIND>(aux, k1 * G.K2 + k2_0 + (long long)j * kThreads));
                     a1.push_batch(x);
-                    emit(a1, out, partial, k1 * G.K2 + k2_0 + (long long)j * kThreads, s, G.nout, G.S, G.fin, divisor, flag);
+                    emit(a1, out, partial, k1 * G.K2 + k2_0 + (long long)j * kThreads, s, G.nout, G.S, G.fin, divisor, flag, G.counters);
                 }
             return;
         } else {
@@ -327,7 +436,7 @@ __global__ void __launch_bounds__(kThreads) reduce_micro_kernel(T *__restrict__ 
     if constexpr (!(R2C > 0 && WIDE)) {  // the WIDE path has emitted and returned above
 #pragma unroll
         for (int j = 0; j < OUTS; ++j)
-            if (live[j]) emit(acc[j], out, partial, k1 * G.K2 + k2_0 + (long long)j * kThreads, s, G.nout, G.S, G.fin, divisor, flag);
+            if (live[j]) emit(acc[j], out, partial, k1 * G.K2 + k2_0 + (long long)j * kThreads, s, G.nout, G.S, G.fin, divisor, flag, G.counters);
     }
 }
 
@@ -403,19 +512,50 @@ __global__ void __launch_bounds__(kThreads) reduce_rows_kernel(T *__restrict__ o
         acc.init((T)0);
     }
     warp_merge(acc);
-    if (lanes == 32) {
-        if (active && lane == 0) emit(acc, out, partial, o, s, G.nout, G.S, G.fin, divisor, flag);
+    const bool fused = (G.S > 1) && G.counters != nullptr;
+    if (lanes == 32) {  // a warp per (output, split)
+        unsigned int last = 0;
+        if (active && lane == 0) {
+            emit(acc, out, partial, o, s, G.nout, G.S, G.fin, divisor, flag, (unsigned int *)nullptr);
+            if (fused) {
+                __threadfence();
+                last = (atomicAdd(&G.counters[o], 1u) == (unsigned int)(G.S - 1));
+            }
+        }
+        if (fused) {
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                __threadfence();
+                warp_combine<T, KIND>(out, partial, o, G.nout, G.S, G.fin, divisor, flag, G.counters, lane);
+            }
+        }
         return;
     }
-    // block per output: merge the eight warp results in warp order
+    // block per (output, split): merge the eight warp results in warp order
+    __shared__ unsigned int s_last;
     const int warp = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) smem[warp] = acc;
     __syncthreads();
-    if (threadIdx.x == 0 && active) {
-        Acc<T, KIND> t = smem[0];
+    if (threadIdx.x == 0) {
+        unsigned int last = 0;
+        if (active) {
+            Acc<T, KIND> t = smem[0];
 #pragma unroll
-        for (int w = 1; w < kThreads / 32; ++w) t.merge(smem[w]);
-        emit(t, out, partial, o, s, G.nout, G.S, G.fin, divisor, flag);
+            for (int w = 1; w < kThreads / 32; ++w) t.merge(smem[w]);
+            emit(t, out, partial, o, s, G.nout, G.S, G.fin, divisor, flag, (unsigned int *)nullptr);
+            if (fused) {
+                __threadfence();
+                last = (atomicAdd(&G.counters[o], 1u) == (unsigned int)(G.S - 1));
+            }
+        }
+        s_last = last;
+    }
+    if (fused) {
+        __syncthreads();
+        if (s_last && warp == 0) {
+            __threadfence();
+            warp_combine<T, KIND>(out, partial, o, G.nout, G.S, G.fin, divisor, flag, G.counters, threadIdx.x & 31);
+        }
     }
 }
 
@@ -582,9 +722,16 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
     }
 
     void *partial = nullptr;
+    G.counters = nullptr;
     if (G.S > 1) {
         int rc = feo_workspace(ctx, (size_t)G.S * (size_t)G.nout * sizeof(Acc<T, KIND>), &partial);
         if (rc != FEO_OK) return rc;
+        // fused combine: the last writer of each output merges its S partials (needs one zeroed counter per output)
+        // Worth it where a launch costs more than the last arriver's serial tail: small inputs (config 1: 13.6 -> 8.6 us);
+        // on multi-GiB inputs the second launch is 0.2 % and the two-stage combine is a little faster.  Knob: 2 = always.
+        const size_t in_bytes = (size_t)c.K1 * c.R1 * c.K2 * c.R2 * sizeof(T);
+        const int fuse = ctx->knobs[FEO_KNOB_REDUCE_FUSE];
+        if (fuse != 1 && (fuse == 2 || in_bytes <= (size_t(256) << 20)) && (size_t)G.nout <= ctx->counters_len) G.counters = ctx->counters;
     }
     int *flag = ctx->arith_flag;
     if (which == COLS) {
@@ -619,7 +766,7 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         else reduce_rows_kernel<T, KIND, L, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
     }
     FEO_LAUNCH_CHECK(ctx);
-    if (G.S > 1) {
+    if (G.S > 1 && !G.counters) {
         if (G.nout < 4096) {
             const long long blocks = feo_ceil_div((size_t)G.nout * 32, (size_t)kThreads);
             reduce_stage2_kernel<T, KIND, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, G.nout, G.S, fin, divisor, flag);

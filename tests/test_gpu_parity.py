@@ -365,15 +365,20 @@ def test_reduction_split_counts_agree(feo, oracle):
             x = rand(oracle, rng, "i64", shape)
             xf = rand(oracle, rng, "f32", shape)
             t, tf = feo.Tensor(feo.Shape(shape), x), feo.Tensor(feo.Shape(shape), xf)
-            for S in (0, 1, 2, 3, 7, 16):
+            for S, fuse_off in ((0, 0), (1, 0), (2, 2), (3, 1), (7, 2), (7, 1), (16, 2), (16, 1), (0, 1), (0, 2)):
                 ctx.tune(L.KNOB_REDUCE_SPLIT, S)
+                ctx.tune(L.KNOB_REDUCE_FUSE, fuse_off)  # fused last-arriver combine vs the two-launch combine: same bits
                 for kind in ("sum", "var", "max", "min", "mean"):
                     np.testing.assert_array_equal(getattr(t, kind)(axes).to_numpy(), oracle.reduce(kind, x, axes), err_msg=f"S={S} {kind} {shape}")
                 np.testing.assert_array_equal(tf.max(axes).to_numpy(), oracle.reduce("max", xf, axes))
+                # float results are deterministic for a given configuration (no atomics on data): same bits every time
+                np.testing.assert_array_equal(tf.sum(axes).to_numpy(), tf.sum(axes).to_numpy())
+                np.testing.assert_array_equal(tf.var(axes).to_numpy(), tf.var(axes).to_numpy())
                 abs_sum, n = _terms(xf, axes)
                 assert_sum_like(tf.sum(axes).to_numpy().reshape(-1), oracle.reduce("sum", xf, axes).reshape(-1), abs_sum, n, "f32")
     finally:
         ctx.tune(L.KNOB_REDUCE_SPLIT, 0)
+        ctx.tune(L.KNOB_REDUCE_FUSE, 0)
 
 
 def test_mean_divisor_quirk_on_device(feo, oracle):

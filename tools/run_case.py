@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--kc", type=int, default=0)
     ap.add_argument("--pdl", type=int, default=0, help="1 = disable programmatic dependent launch")
     ap.add_argument("--slabs", type=int, default=1)
+    ap.add_argument("--nofuse", type=int, default=0, help="1 = two-launch combine for split reductions")
     ap.add_argument("--l2keep", type=int, default=0, help="1 = disable the evict_last policy on broadcast operands")
     args = ap.parse_args()
 
@@ -55,6 +56,7 @@ def main():
     ctx.tune(L.KNOB_BCAST_LCHUNK, args.lchunk)
     ctx.tune(L.KNOB_MATMUL_TF32_KC, args.kc)
     ctx.tune(L.KNOB_PDL, args.pdl)
+    ctx.tune(L.KNOB_REDUCE_FUSE, args.nofuse)
     ctx.tune(L.KNOB_BCAST_L2KEEP, args.l2keep)
     lib, h, vp = ctx.lib, ctx.handle, C.c_void_p
     dt = L.code_of(args.dtype)
