@@ -20,7 +20,7 @@
 namespace feo_red {
 
 constexpr int kThreads = 256;
-enum { K_SUM = 0, K_MAX = 1, K_MIN = 2, K_WELFORD = 3, K_SQDEV = 4 };
+enum { K_SUM = 0, K_MAX = 1, K_MIN = 2, K_WELFORD = 3, K_SQDEV = 4, K_INTVAR = 5 };
 enum { FIN_NONE = 0, FIN_DIV = 1, FIN_VAR = 2, FIN_MEAN_M2 = 3 };
 enum { LD_PLAIN = 0, LD_MUL = 1, LD_MATVEC = 2, LD_VECMAT = 3 };
 
@@ -111,6 +111,25 @@ template <typename T> struct Acc<T, K_MIN> {
         }
     }
 };
+// Integer variance of ONE complete batch (the whole reduced range of an output sits in a thread's registers: the
+// single-row micro geometry): the reference's two passes (tensor.rs:171-177, 188-202) fused -- truncated integer mean,
+// wrapping squares.  Only push_batch is meaningful; the planner uses this kind nowhere else.
+template <typename T> struct Acc<T, K_INTVAR> {
+    T v, n;
+    __device__ __forceinline__ void init(T divisor) { v = (T)0; n = divisor; }
+    __device__ __forceinline__ void push(T) {}
+    __device__ __forceinline__ void merge(const Acc &) {}
+    template <int N> __device__ __forceinline__ void push_batch(const T (&x)[N]) {
+        T s = (T)0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) s = w_add(s, x[i]);
+        const T mean = w_div(s, n, (int *)nullptr);
+        T q = (T)0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { const T c = w_sub(x[i], mean); q = w_add(q, w_mul(c, c)); }
+        v = q;
+    }
+};
 // Welford / Chan: (count, mean, M2).  Batches are combined two-pass in registers and merged with one
 // division per batch, so the per-element cost stays ~4 flops while keeping Welford's stability.
 template <typename T> struct Acc<T, K_WELFORD> {
@@ -160,6 +179,8 @@ template <typename T, int KIND> __device__ __forceinline__ Acc<T, KIND> shfl_dow
         r.n = shfl_down_t(a.n, off); r.mean = shfl_down_t(a.mean, off); r.m2 = shfl_down_t(a.m2, off);
     } else if constexpr (KIND == K_SQDEV) {
         r.v = shfl_down_t(a.v, off); r.m = a.m;
+    } else if constexpr (KIND == K_INTVAR) {
+        r.v = shfl_down_t(a.v, off); r.n = a.n;
     } else {
         r.v = shfl_down_t(a.v, off);
     }
@@ -216,16 +237,22 @@ __device__ __noinline__ void combine_thread(T *out, const void *partial, long lo
 // Result of one (output, split) pair, thread level (cols / micro kernels).  S == 1: final value.  S > 1: the accumulator
 // goes to the workspace; with `counters` the LAST of the S writers of this output merges all S partials in split order
 // (so the result does not depend on who is last) and finalises -- one launch instead of two, no atomics on data.
+// The S > 1 path is out of line (by-value accumulator) so that it does not inflate the streaming kernels' registers.
 template <typename T, int KIND>
-__device__ __forceinline__ void emit(const Acc<T, KIND> &acc, T *out, void *partial, long long o, long long s, long long nout,
-                                     long long S, int fin, T divisor, int *flag, unsigned int *counters) {
-    if (S <= 1) { finalize(acc, out, o, nout, fin, divisor, flag); return; }
+__device__ __noinline__ void publish_partial(Acc<T, KIND> acc, T *out, void *partial, long long o, long long s, long long nout, long long S,
+                                             int fin, T divisor, int *flag, unsigned int *counters) {
     reinterpret_cast<Acc<T, KIND> *>(partial)[s * nout + o] = acc;
     if (!counters) return;  // two-stage mode: reduce_stage2_kernel combines
     __threadfence();
     const unsigned int ticket = atomicAdd(&counters[o], 1u);
     if (ticket != (unsigned int)(S - 1)) return;
     combine_thread<T, KIND>(out, partial, o, nout, S, fin, divisor, flag, counters);
+}
+template <typename T, int KIND>
+__device__ __forceinline__ void emit(const Acc<T, KIND> &acc, T *out, void *partial, long long o, long long s, long long nout,
+                                     long long S, int fin, T divisor, int *flag, unsigned int *counters) {
+    if (S <= 1) finalize(acc, out, o, nout, fin, divisor, flag);
+    else publish_partial<T, KIND>(acc, out, partial, o, s, nout, S, fin, divisor, flag, counters);
 }
 
 // Warp-level merge of the S partials of output o (same order as reduce_stage2_kernel<WARP>): every lane of the calling
@@ -266,7 +293,7 @@ struct Geom {
 
 // ---- cols: in[k1][r1][k2] -> out[k1][k2], threads along k2 ---------------------------------------------
 template <typename T, int KIND, int LOADER, bool VEC>
-__global__ void __launch_bounds__(kThreads) reduce_cols_kernel(T *__restrict__ out, void *__restrict__ partial,
+__global__ void __launch_bounds__(kThreads, 3) reduce_cols_kernel(T *__restrict__ out, void *__restrict__ partial,
                                                                const T *__restrict__ in, const T *__restrict__ in2,
                                                                const T *__restrict__ aux, const __grid_constant__ Geom G,
                                                                T divisor, int *flag) {
@@ -376,9 +403,9 @@ __global__ void __launch_bounds__(kThreads) reduce_micro_kernel(T *__restrict__ 
 #pragma unroll
                         for (int k = 0; k < W; ++k) x[i * W + k] = v[j][i].v[k];
                     Acc<T, KIND> a1;
-                    a1.init(aux_val<KIND>(aux, k1 * G.K2 + k2_0 + (long long)j * kThreads));
+                    a1.init(KIND == K_INTVAR ? divisor : aux_val<KIND>(aux, k1 * G.K2 + k2_0 + (long long)j * kThreads));
                     a1.push_batch(x);
-                    emit(a1, out, partial, k1 * G.K2 + k2_0 + (long long)j * kThreads, s, G.nout, G.S, G.fin, divisor, flag, G.counters);
+                    finalize(a1, out, k1 * G.K2 + k2_0 + (long long)j * kThreads, G.nout, G.fin, divisor, flag);  // r1 == 1: never split
                 }
             return;
         } else {
@@ -442,7 +469,7 @@ __global__ void __launch_bounds__(kThreads) reduce_micro_kernel(T *__restrict__ 
 
 // ---- rows: in[k1][r1][k2][r2], long r2; `lanes` threads cooperate on one output ----------------------------
 template <typename T, int KIND, int LOADER, bool VEC>
-__global__ void __launch_bounds__(kThreads) reduce_rows_kernel(T *__restrict__ out, void *__restrict__ partial,
+__global__ void __launch_bounds__(kThreads, 4) reduce_rows_kernel(T *__restrict__ out, void *__restrict__ partial,
                                                                const T *__restrict__ in, const T *__restrict__ in2,
                                                                const T *__restrict__ aux, const __grid_constant__ Geom G,
                                                                T divisor, int *flag) {
@@ -721,6 +748,9 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         G.S1 = S1; G.S2 = S2; G.S = S1 * S2; G.c2 = c2;
     }
 
+    if constexpr (KIND == K_INTVAR) {  // only the single-batch geometry can fuse the two integer passes
+        if (!(which == MICRO && c.R1 == 1 && r2c > 0)) return -1;
+    }
     void *partial = nullptr;
     G.counters = nullptr;
     if (G.S > 1) {

@@ -78,6 +78,13 @@ int reduce_typed(feo_ctx *ctx, int kind, T *out, const T *in, const T *aux, int 
             return run_plan<T, K_WELFORD>(ctx, p, out, in, nullptr, partial ? FIN_MEAN_M2 : FIN_VAR, n);
         } else {
             // tensor.rs:188,196-202 in integers: mean = sum / n (truncating), then sum (x - mean)^2 / n
+            if (!partial) {  // short reduced innermost axis: both passes in registers, one kernel
+                const Canon c = canonicalise(p.m, p.ext, p.red);
+                if (c.ok) {
+                    const int rc1 = run_canonical<T, K_INTVAR, LD_PLAIN>(ctx, c, out, in, nullptr, nullptr, FIN_DIV, n);
+                    if (rc1 != -1) return rc1;
+                }
+            }
             T *mean = nullptr;
             FEO_CUDA(ctx, cudaMallocAsync((void **)&mean, (size_t)p.nout * sizeof(T), ctx->stream));
             int rc = run_plan<T, K_SUM>(ctx, p, mean, in, nullptr, FIN_DIV, n);
