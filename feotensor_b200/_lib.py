@@ -32,6 +32,8 @@ _vp, _sz, _int = C.c_void_p, C.c_size_t, C.c_int
 _szp = C.POINTER(C.c_size_t)
 
 # name -> (restype, argtypes); must list every FEO_API symbol of include/feotensor_b200.h
+PEER_HANDLE_BYTES, MAX_PEERS = 64, 8
+
 SIGNATURES = {
     "feo_abi_version": (_int, []),
     "feo_dtype_size": (_sz, [_int]),
@@ -45,6 +47,7 @@ SIGNATURES = {
     "feo_tune": (_int, [_vp, _int, _int]),
     "feo_malloc": (_int, [_vp, _sz, C.POINTER(_vp)]),
     "feo_free": (_int, [_vp, _vp]),
+    "feo_trim": (_int, [_vp]),
     "feo_host_alloc": (_int, [_vp, _sz, C.POINTER(_vp)]),
     "feo_host_free": (_int, [_vp, _vp]),
     "feo_upload": (_int, [_vp, _vp, _vp, _sz]),
@@ -74,6 +77,20 @@ SIGNATURES = {
     "feo_matvec": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _sz]),
     "feo_vecmat": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _sz]),
     "feo_matmul": (_int, [_vp, _int, _int, _vp, _vp, _vp, _sz, _sz, _sz]),
+    "feo_peer_alloc": (_int, [_vp, _sz, C.POINTER(_vp)]),
+    "feo_peer_free": (_int, [_vp, _vp]),
+    "feo_peer_export": (_int, [_vp, _vp, C.c_char_p]),
+    "feo_peer_open": (_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "feo_peer_close": (_int, [_vp, _vp]),
+    "feo_comm_create": (_int, [_vp, _int, _int, C.POINTER(_vp), _sz, C.POINTER(_vp)]),
+    "feo_comm_destroy": (_int, [_vp]),
+    "feo_comm_slot": (_int, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
+    "feo_comm_barrier": (_int, [_vp]),
+    "feo_comm_allreduce": (_int, [_vp, _int, _int, _vp, _sz, _sz, _vp]),
+    "feo_reduce_sharded": (_int, [_vp, _int, _int, _vp, _vp, _int, _szp, _int, _szp, _vp]),
+    "feo_comm_gather": (_int, [_vp, _vp, C.POINTER(_vp), _sz]),
+    "feo_matmul_sharded_b": (_int, [_vp, _int, _int, _vp, _vp, C.POINTER(_vp), _sz, _sz, _sz]),
+    "feo_dot_sharded": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _sz]),
 }
 
 _lib = None

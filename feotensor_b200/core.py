@@ -83,6 +83,10 @@ class Context:
         if ptr and self.handle:
             self.lib.feo_free(self.handle, C.c_void_p(ptr))
 
+    def trim(self):
+        """Synchronise and hand the pool's cached (freed) blocks back to the driver."""
+        self.check(self.lib.feo_trim(self.handle))
+
     def upload(self, dst: int, host: np.ndarray):
         host = np.ascontiguousarray(host)
         self.check(self.lib.feo_upload(self.handle, C.c_void_p(dst), host.ctypes.data_as(C.c_void_p), host.nbytes))

@@ -35,13 +35,18 @@ bool feo_pdl_admit(feo_ctx *ctx) {
     return independent;
 }
 
+cudaError_t feo_alloc_async(feo_ctx *ctx, void **ptr, size_t bytes) {
+    if (ctx->pool) return cudaMallocFromPoolAsync(ptr, bytes, ctx->pool, ctx->stream);
+    return cudaMallocAsync(ptr, bytes, ctx->stream);
+}
+
 int feo_workspace(feo_ctx *ctx, size_t bytes, void **ptr) {
     if (bytes > ctx->workspace_bytes) {
         if (ctx->workspace) FEO_CUDA(ctx, cudaFreeAsync(ctx->workspace, ctx->stream));
         ctx->workspace = nullptr;
         ctx->workspace_bytes = 0;
         size_t want = bytes < (size_t(8) << 20) ? (size_t(8) << 20) : bytes;
-        FEO_CUDA(ctx, cudaMallocAsync(&ctx->workspace, want, ctx->stream));
+        FEO_CUDA(ctx, feo_alloc_async(ctx, &ctx->workspace, want));
         ctx->workspace_bytes = want;
     }
     *ptr = ctx->workspace;
@@ -74,6 +79,21 @@ int feo_init(int device, feo_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FEO_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
+    {
+        // own pool; keep freed blocks cached across synchronisations (the default pool trims to 0 at every sync)
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            ctx->pool = nullptr;  // plain cudaMallocAsync from the device's default pool
+            cudaGetLastError();
+        }
+    }
     if (cudaMalloc(&ctx->arith_flag, sizeof(int)) != cudaSuccess || cudaMemset(ctx->arith_flag, 0, sizeof(int)) != cudaSuccess) {
         cudaStreamDestroy(ctx->own_stream);
         delete ctx;
@@ -93,7 +113,9 @@ int feo_shutdown(feo_ctx *ctx) {
     if (!ctx) return FEO_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->workspace) cudaFree(ctx->workspace);
+    if (ctx->workspace) cudaFreeAsync(ctx->workspace, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->arith_flag) cudaFree(ctx->arith_flag);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -125,11 +147,17 @@ int feo_tune(feo_ctx *ctx, int knob, int value) {
 int feo_malloc(feo_ctx *ctx, size_t bytes, void **dptr) {
     if (!dptr) return feo_fail(ctx, FEO_ERR_SHAPE, "null output pointer");
     *dptr = nullptr;
-    FEO_CUDA(ctx, cudaMallocAsync(dptr, bytes ? bytes : 1, ctx->stream));
+    FEO_CUDA(ctx, feo_alloc_async(ctx, dptr, bytes ? bytes : 1));
     return FEO_OK;
 }
 int feo_free(feo_ctx *ctx, void *dptr) {
     if (dptr) FEO_CUDA(ctx, cudaFreeAsync(dptr, ctx->stream));  // stream-ordered: takes effect after every earlier kernel
+    return FEO_OK;
+}
+int feo_trim(feo_ctx *ctx) {
+    if (!ctx) return FEO_ERR_SHAPE;
+    FEO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->pool) FEO_CUDA(ctx, cudaMemPoolTrimTo(ctx->pool, 0));
     return FEO_OK;
 }
 int feo_host_alloc(feo_ctx *ctx, size_t bytes, void **hptr) {

@@ -34,6 +34,7 @@ struct feo_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;      // stream in use
     cudaStream_t own_stream = nullptr;  // stream created by feo_init
+    cudaMemPool_t pool = nullptr;       // this context's own stream-ordered pool (never trimmed at synchronisation)
     void *workspace = nullptr;          // scratch for two-stage reductions
     size_t workspace_bytes = 0;
     int *arith_flag = nullptr;          // device int, sticky
@@ -52,6 +53,9 @@ int feo_fail(feo_ctx *ctx, int status, const char *fmt, ...);
 // WAW overlap with any of them, window not full); records it.  False: launch normally (full stream order).
 bool feo_pdl_admit(feo_ctx *ctx);
 int feo_workspace(feo_ctx *ctx, size_t bytes, void **ptr);
+// Stream-ordered allocation from the context's own pool.  A private pool means a block freed on another context's stream
+// is never handed out here with a hidden cross-stream dependency -- which would deadlock kernels that wait for peers.
+cudaError_t feo_alloc_async(feo_ctx *ctx, void **ptr, size_t bytes);
 
 #define FEO_CUDA(ctx, expr)                                                                       \
     do {                                                                                          \

@@ -27,6 +27,7 @@
 #include <cuda.h>
 
 #include "feo_common.cuh"
+#include "peer_sync.cuh"
 
 namespace {
 
@@ -294,6 +295,60 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(float *__restrict_
     }
 }
 
+// The same for a B that is row-sharded across GPUs (all-gather of B -> matmul, fused): the panels stay where
+// they are and this kernel pulls them over NVLink while it splits and transposes -- no gathered copy of B is ever written.
+// Tile = 32 k-rows x 128 n-columns; every lane loads 16 bytes along n (512 contiguous bytes per warp request, all four of
+// a thread's requests in flight before the first use) and stores 16 bytes along k.
+constexpr int GT_K = 32, GT_N = 128;
+__global__ void __launch_bounds__(256) split_transpose_gather_kernel(float *__restrict__ hi, float *__restrict__ lo,
+                                                                     const __grid_constant__ feo_peer::BParts parts,
+                                                                     const __grid_constant__ feo_peer::XchgParams sync, int K, int N, int Kp,
+                                                                     bool vec) {
+    __shared__ float tile[GT_K][GT_N + 1];
+    feo_peer::signal_and_wait(sync);
+    const int k0 = blockIdx.y * GT_K, n0 = blockIdx.x * GT_N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int k = k0 + warp * 4 + j, n = n0 + lane * 4;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K) {
+            const int r = k / parts.rows_per_part;
+            const float *row = parts.part[r] + (size_t)(k - r * parts.rows_per_part) * N;
+            if (vec && n + 3 < N) {
+                v[j] = feo_peer::ld_peer(reinterpret_cast<const float4 *>(row + n));
+            } else {
+                float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (n + c < N) t[c] = feo_peer::ld_peer(row + n + c);
+                v[j] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float *dst = &tile[warp * 4 + j][lane * 4];
+        dst[0] = v[j].x; dst[1] = v[j].y; dst[2] = v[j].z; dst[3] = v[j].w;
+    }
+    __syncthreads();
+    // thread -> (n = pass * 32 + tid / 8, four k at (tid % 8) * 4): 128-byte rows of Bt, conflict-free column reads
+    const int kq = (threadIdx.x & 7) * 4;
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+        const int nl = pass * 32 + (threadIdx.x >> 3);
+        if (n0 + nl < N) {
+            float4 h, l;
+            split1(tile[kq + 0][nl], h.x, l.x); split1(tile[kq + 1][nl], h.y, l.y);
+            split1(tile[kq + 2][nl], h.z, l.z); split1(tile[kq + 3][nl], h.w, l.w);
+            const size_t o = (size_t)(n0 + nl) * Kp + k0 + kq;
+            *reinterpret_cast<float4 *>(hi + o) = h;
+            *reinterpret_cast<float4 *>(lo + o) = l;
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -330,8 +385,11 @@ bool feo_matmul_tf32x3_supported(size_t M, size_t K, size_t N) {
     return M >= 1 && N >= 1 && K >= 1 && M < lim && N < lim && K < lim - BK && M * N * K >= (size_t(1) << 21);
 }
 
-int feo_impl_matmul_tf32x3(feo_ctx *ctx, void *C, const void *A, const void *B, size_t M, size_t K, size_t N) {
-    if (!feo_aligned16(A) || !feo_aligned16(B) || !feo_aligned16(C)) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "TF32X3 needs 16-byte aligned operands");
+namespace {
+
+int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const feo_peer::BParts *parts, const feo_peer::XchgParams *sync,
+                      size_t M, size_t K, size_t N) {
+    if (!feo_aligned16(A) || !feo_aligned16(C) || (B && !feo_aligned16(B))) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "TF32X3 needs 16-byte aligned operands");
     static bool attr_set = false;
     if (!attr_set) {
         FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -349,7 +407,14 @@ int feo_impl_matmul_tf32x3(feo_ctx *ctx, void *C, const void *A, const void *B, 
     if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
     split_rows_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a_hi, a_lo, (const float *)A, (int)M, (int)K, (int)Kp, K % 4 == 0);
     FEO_LAUNCH_CHECK(ctx);
-    split_transpose_kernel<<<dim3((unsigned)feo_ceil_div(N, (size_t)32), (unsigned)(Kp / 32)), 256, 0, ctx->stream>>>(b_hi, b_lo, (const float *)B, (int)K, (int)N, (int)Kp);
+    if (parts) {
+        bool vec = N % 4 == 0;
+        for (int r = 0; r < parts->world; ++r) vec = vec && feo_aligned16(parts->part[r]);
+        split_transpose_gather_kernel<<<dim3((unsigned)feo_ceil_div(N, (size_t)GT_N), (unsigned)(Kp / GT_K)), 256, 0, ctx->stream>>>(
+            b_hi, b_lo, *parts, *sync, (int)K, (int)N, (int)Kp, vec);
+    } else {
+        split_transpose_kernel<<<dim3((unsigned)feo_ceil_div(N, (size_t)32), (unsigned)(Kp / 32)), 256, 0, ctx->stream>>>(b_hi, b_lo, (const float *)B, (int)K, (int)N, (int)Kp);
+    }
     FEO_LAUNCH_CHECK(ctx);
 
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
@@ -364,4 +429,15 @@ int feo_impl_matmul_tf32x3(feo_ctx *ctx, void *C, const void *A, const void *B, 
     matmul_tf32x3_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, (float *)C, (int)M, (int)N, (int)(Kp / BK), kc);
     FEO_LAUNCH_CHECK(ctx);
     return FEO_OK;
+}
+
+}  // namespace
+
+int feo_impl_matmul_tf32x3(feo_ctx *ctx, void *C, const void *A, const void *B, size_t M, size_t K, size_t N) {
+    return matmul_tf32x3_run(ctx, C, A, B, nullptr, nullptr, M, K, N);
+}
+
+int feo_impl_matmul_tf32x3_parts(feo_ctx *ctx, void *C, const void *A, const feo_peer::BParts &parts, const feo_peer::XchgParams &sync,
+                                 size_t M, size_t K, size_t N) {
+    return matmul_tf32x3_run(ctx, C, A, nullptr, &parts, &sync, M, K, N);
 }

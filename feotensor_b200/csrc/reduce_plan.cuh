@@ -86,7 +86,7 @@ int reduce_typed(feo_ctx *ctx, int kind, T *out, const T *in, const T *aux, int 
                 }
             }
             T *mean = nullptr;
-            FEO_CUDA(ctx, cudaMallocAsync((void **)&mean, (size_t)p.nout * sizeof(T), ctx->stream));
+            FEO_CUDA(ctx, feo_alloc_async(ctx, (void **)&mean, (size_t)p.nout * sizeof(T)));
             int rc = run_plan<T, K_SUM>(ctx, p, mean, in, nullptr, FIN_DIV, n);
             if (rc == FEO_OK) rc = run_plan<T, K_SQDEV>(ctx, p, out, in, mean, FIN_DIV, n);
             cudaFreeAsync(mean, ctx->stream);

@@ -13,6 +13,11 @@ A ShardedTensor is one dense row-major block of leading rows per rank.  Which op
   dot                                                 all-reduce(SUM) of per-shard partial dots
   matmul (A row-sharded)                              none if B is replicated, else all-gather of B
 
+With a `PeerComm` attached to the engine (`CudaEngine(comm=PeerComm(...))`) the exchange steps above do not call
+NCCL: the local reduction writes its partial straight into a peer-mapped window and ONE kernel per rank signals, waits
+and combines the partials over NVLink in rank order with the epilogue (mean's division, var's Chan merge) fused in
+(`csrc/peer.cu`).  torch.distributed then only carries the 64-byte IPC handles at start-up.
+
 The local arithmetic goes through an *engine*: `CudaEngine` (the C ABI; the only engine this package ships) --
 the CPU tests inject their own checker engine to exercise exactly this exchange logic under gloo.
 """
@@ -30,15 +35,120 @@ def _dist():
     return dist
 
 
+class PeerComm:
+    """The `world` peer-mapped windows of one node and the native exchange kernels over them (csrc/peer.cu).
+
+    `windows=` lets a test hand in raw device addresses (several ranks inside one process on one GPU); the normal
+    constructor allocates this rank's window, exchanges CUDA IPC handles through torch.distributed and opens the peers'."""
+
+    def __init__(self, ctx, rank=None, world=None, group=None, window_bytes=4 << 20, windows=None):
+        self.ctx, self.lib = ctx, ctx.lib
+        self._opened, self._own = [], None
+        if windows is None:
+            dist = _dist()
+            rank = dist.get_rank(group) if rank is None else rank
+            world = dist.get_world_size(group) if world is None else world
+            p = C.c_void_p()
+            ctx.check(self.lib.feo_peer_alloc(ctx.handle, window_bytes, C.byref(p)))
+            self._own = p.value
+            handle = C.create_string_buffer(L.PEER_HANDLE_BYTES)
+            ctx.check(self.lib.feo_peer_export(ctx.handle, p, handle))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            windows = []
+            for r in range(world):
+                if r == rank:
+                    windows.append(self._own)
+                    continue
+                q = C.c_void_p()
+                ctx.check(self.lib.feo_peer_open(ctx.handle, handles[r], C.byref(q)))
+                self._opened.append(q.value)
+                windows.append(q.value)
+            dist.barrier(group=group)  # every window is zeroed and mapped before the first signal
+        self.rank, self.world, self.window_bytes = int(rank), int(world), int(window_bytes)
+        arr = (C.c_void_p * self.world)(*[C.c_void_p(w) for w in windows])
+        h = C.c_void_p()
+        ctx.check(self.lib.feo_comm_create(ctx.handle, self.rank, self.world, arr, self.window_bytes, C.byref(h)))
+        self.handle = h
+
+    def slot(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self.ctx.check(self.lib.feo_comm_slot(self.handle, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def barrier(self):
+        self.ctx.check(self.lib.feo_comm_barrier(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.ctx.sync()
+            self.lib.feo_comm_destroy(self.handle)
+            self.handle = None
+            for q in self._opened:
+                self.lib.feo_peer_close(self.ctx.handle, C.c_void_p(q))
+            if self._own:
+                self.lib.feo_peer_free(self.ctx.handle, C.c_void_p(self._own))
+            self._opened, self._own = [], None
+
+
+class PeerBuffer:
+    """One device allocation per rank that every rank can read: `ptrs[r]` is rank r's block as mapped in this process.
+
+    Holds operands that a fused kernel pulls over NVLink (the row panels of a sharded B, `feo_matmul_sharded_b`).
+    `ptrs=` hands in raw addresses (single-process tests); otherwise the handles travel through torch.distributed."""
+
+    def __init__(self, ctx, nbytes, rank=None, world=None, group=None, ptrs=None):
+        self.ctx, self.lib, self.nbytes = ctx, ctx.lib, int(nbytes)
+        self._opened, self._own = [], None
+        if ptrs is None:
+            dist = _dist()
+            rank = dist.get_rank(group) if rank is None else rank
+            world = dist.get_world_size(group) if world is None else world
+            p = C.c_void_p()
+            ctx.check(self.lib.feo_peer_alloc(ctx.handle, self.nbytes, C.byref(p)))
+            self._own = p.value
+            handle = C.create_string_buffer(L.PEER_HANDLE_BYTES)
+            ctx.check(self.lib.feo_peer_export(ctx.handle, p, handle))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            ptrs = []
+            for r in range(world):
+                if r == rank:
+                    ptrs.append(self._own)
+                    continue
+                q = C.c_void_p()
+                ctx.check(self.lib.feo_peer_open(ctx.handle, handles[r], C.byref(q)))
+                self._opened.append(q.value)
+                ptrs.append(q.value)
+        self.rank, self.world, self.ptrs = int(rank), int(world), [int(q) for q in ptrs]
+
+    def tensor(self, dims, dtype):
+        """This rank's block viewed as a dense row-major tensor (no copy)."""
+        from .core import DeviceStorage, Shape, Tensor
+        shp = Shape(list(dims))
+        if shp.size() * L.np_dtype(dtype).itemsize > self.nbytes:
+            raise ValueError("the buffer is smaller than the tensor")
+        return Tensor._wrap(shp, DeviceStorage(self.ctx, shp.size(), dtype, ptr=self.ptrs[self.rank], owner=self))
+
+    def close(self):
+        self.ctx.sync()
+        for q in self._opened:
+            self.lib.feo_peer_close(self.ctx.handle, C.c_void_p(q))
+        if self._own:
+            self.lib.feo_peer_free(self.ctx.handle, C.c_void_p(self._own))
+        self._opened, self._own = [], None
+
+
 class CudaEngine:
     """Local compute on this rank's GPU through libfeotensor_b200 (arrays are core.Tensor)."""
 
-    def __init__(self, ctx=None):
+    def __init__(self, ctx=None, comm=None):
         import torch
 
         from .core import Context
         self.torch = torch
         self.ctx = ctx or Context.default()
+        self.comm = comm  # PeerComm: exchanges run as native peer-memory kernels instead of NCCL calls
         # one stream for the library and for torch's collectives, so NCCL is ordered after the kernels
         self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 
@@ -107,6 +217,23 @@ class CudaEngine:
                                         nparts, nout, count_per_part, d.ctypes.data_as(C.c_void_p)))
         return out
 
+    def reduce_sharded(self, kind, x, local_axes, nout, divisor):
+        """Local reduction + peer-memory exchange + epilogue in one stream-ordered native sequence (csrc/peer.cu)."""
+        ctx, dims = self.ctx, self.dims(x)
+        out = self.empty([nout], x.dtype)
+        d = np.array([divisor], dtype=x.dtype)
+        ctx.check(ctx.lib.feo_reduce_sharded(self.comm.handle, L.KIND_CODES[kind], x.data.code, C.c_void_p(out.data.ptr),
+                                             C.c_void_p(x.data.ptr), len(dims), L.sizes(dims), len(local_axes), L.sizes(local_axes),
+                                             d.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def dot_sharded(self, a, b):
+        ctx = self.ctx
+        out = self.empty([1], a.dtype)
+        ctx.check(ctx.lib.feo_dot_sharded(self.comm.handle, a.data.code, C.c_void_p(out.data.ptr), C.c_void_p(a.data.ptr),
+                                          C.c_void_p(b.data.ptr), 1, a.size()))
+        return out
+
     def dot(self, a, b):
         from .core import Vector
         return Vector.from_tensor(a).vecmul(Vector.from_tensor(b))._tensor
@@ -117,6 +244,15 @@ class CudaEngine:
     def matmul(self, A, B, algo="auto"):
         from .core import Matrix
         return Matrix.from_tensor(A).matmul(Matrix.from_tensor(B), algo=algo)._tensor
+
+    def matmul_sharded_b(self, A, b_ptrs, K, N, algo="auto"):
+        """A[M,K] (this rank's rows) times a B whose row panels sit in peer memory: gather fused into the kernel's pre-pass."""
+        ctx, M = self.ctx, self.dims(A)[0]
+        out = self.empty([M, N], A.dtype)
+        arr = (C.c_void_p * len(b_ptrs))(*[C.c_void_p(q) for q in b_ptrs])
+        ctx.check(ctx.lib.feo_matmul_sharded_b(self.comm.handle, L.ALGO_CODES[algo], A.data.code, C.c_void_p(out.data.ptr),
+                                               C.c_void_p(A.data.ptr), arr, M, K, N))
+        return out
 
     def reshape(self, x, dims):
         from .core import Shape, Tensor
@@ -199,6 +335,10 @@ class ShardedTensor:
         if b_sharded:
             if not isinstance(B, ShardedTensor) or B.global_dims[0] != self.global_dims[1]:
                 raise ValueError("assertion `left == right` failed (inner dimensions)")
+            peer = getattr(B, "peer", None)
+            if getattr(eng, "comm", None) is not None and peer is not None:
+                out_local = eng.matmul_sharded_b(self.local, peer.ptrs, B.global_dims[0], B.global_dims[1], algo)
+                return self._like(out_local, [self.global_dims[0], B.global_dims[1]])
             mine = eng.as_torch(B.local)
             full = eng.empty(B.global_dims, eng.dtype(B.local))
             dist.all_gather(list(eng.as_torch(full).view(self.world, -1).unbind(0)), mine, group=self.group)
@@ -225,6 +365,10 @@ class ShardedTensor:
         local_axes = axes if axes else list(range(len(self.global_dims)))
         n_div = reduce_divisor(dtype, self.global_dims, axes)
         is_float = dtype.kind == "f"
+        comm = getattr(eng, "comm", None)
+        if comm is not None and kind in ("sum", "mean", "var", "max", "min") and \
+                nout * dtype.itemsize * (2 if kind == "var" and is_float else 1) <= comm.slot()[1]:
+            return eng.reshape(eng.reduce_sharded(kind, self.local, local_axes, nout, n_div), out_dims)
 
         def allreduce(t, op):
             if dtype == np.uint32 and op != "sum":  # order-preserving bias for the int32 view
@@ -263,16 +407,27 @@ class ShardedTensor:
         eng = self.engine
         if rhs.global_dims != self.global_dims or len(self.global_dims) != 1:
             raise ValueError("assertion failed: self.shape() == rhs.shape()")
+        if getattr(eng, "comm", None) is not None:
+            return eng.dot_sharded(self.local, rhs.local)
         part = eng.dot(self.local, rhs.local)
         _dist().all_reduce(eng.as_torch(part), group=self.group)
         return part
 
 
-def shard_rows(engine, full_host: np.ndarray, rank=None, world=None, group=None):
-    """Upload this rank's block of leading rows of a host array (test / example helper)."""
+def shard_rows(engine, full_host: np.ndarray, rank=None, world=None, group=None, peer=False):
+    """Upload this rank's block of leading rows of a host array (test / example helper).
+
+    peer=True places the block in a PeerBuffer (readable by every rank; `.peer` on the result)."""
     dist = _dist()
     rank = dist.get_rank(group) if rank is None else rank
     world = dist.get_world_size(group) if world is None else world
     rows = full_host.shape[0] // world
     block = np.ascontiguousarray(full_host[rank * rows:(rank + 1) * rows])
-    return ShardedTensor(engine, engine.from_host(block), list(full_host.shape), rank, world, group)
+    if not peer:
+        return ShardedTensor(engine, engine.from_host(block), list(full_host.shape), rank, world, group)
+    buf = PeerBuffer(engine.ctx, block.nbytes, rank, world, group)
+    local = buf.tensor(block.shape, block.dtype)
+    engine.ctx.upload(local.data.ptr, block.reshape(-1))
+    st = ShardedTensor(engine, local, list(full_host.shape), rank, world, group)
+    st.peer = buf
+    return st

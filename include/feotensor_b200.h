@@ -80,6 +80,9 @@ FEO_API int feo_tune(feo_ctx *ctx, int knob, int value);
  * DynamicStorage, storage.rs:7-15). */
 FEO_API int feo_malloc(feo_ctx *ctx, size_t bytes, void **dptr);
 FEO_API int feo_free(feo_ctx *ctx, void *dptr);
+/* feo_malloc / feo_free are stream-ordered on the context's own memory pool, which keeps freed blocks
+ * for reuse; feo_trim synchronises the stream and returns the cached blocks to the driver. */
+FEO_API int feo_trim(feo_ctx *ctx);
 /* Pinned host staging buffers for uploads / downloads. */
 FEO_API int feo_host_alloc(feo_ctx *ctx, size_t bytes, void **hptr);
 FEO_API int feo_host_free(feo_ctx *ctx, void *hptr);
@@ -173,6 +176,53 @@ FEO_API int feo_vecmat(feo_ctx *ctx, int dtype, void *out, const void *v, const 
 /* DynamicMatrix::matmul (matrix.rs:76-90): C[M,N] = A[M,K] * B[K,N], all row-major.  The caller has
  * checked A.cols == B.rows (the reference assert_eq!s, matrix.rs:78). */
 FEO_API int feo_matmul(feo_ctx *ctx, int algo, int dtype, void *C, const void *A, const void *B, size_t M, size_t K, size_t N);
+
+/* ---- cross-GPU epilogues over peer memory (one process per GPU, one node) -------- */
+/* The exchange step after a sharded reduction / dot, as ONE kernel per rank that signals, waits and
+ * combines over NVLink peer loads in rank order (deterministic, bit-identical on every rank) with
+ * the operation's epilogue (mean: / n; var: Chan merge, / n) fused in -- instead of an NCCL call.
+ * Every rank allocates a window, exports its 64-byte handle, opens the peers' handles (the host's
+ * rendezvous carries them; torch.distributed in this repo) and builds a feo_comm from the `world`
+ * window addresses.  All ranks must issue the same sequence of comm calls. */
+#define FEO_MAX_PEERS 8
+#define FEO_PEER_HANDLE_BYTES 64
+typedef struct feo_comm feo_comm;
+/* Zero-filled, IPC-exportable device memory (plain allocation, not the stream-ordered pool). */
+FEO_API int feo_peer_alloc(feo_ctx *ctx, size_t bytes, void **dptr);
+FEO_API int feo_peer_free(feo_ctx *ctx, void *dptr);
+FEO_API int feo_peer_export(feo_ctx *ctx, void *dptr, unsigned char *handle /* [FEO_PEER_HANDLE_BYTES] */);
+/* Maps another process's allocation (enables peer access when it lives on another GPU). */
+FEO_API int feo_peer_open(feo_ctx *ctx, const unsigned char *handle, void **dptr);
+FEO_API int feo_peer_close(feo_ctx *ctx, void *dptr);
+/* windows[r] = address of rank r's window in THIS process (windows[rank] is the local one). */
+FEO_API int feo_comm_create(feo_ctx *ctx, int rank, int world, void *const *windows, size_t window_bytes, feo_comm **comm);
+FEO_API int feo_comm_destroy(feo_comm *comm);
+/* Where this rank's partial for the NEXT exchange goes (inside its own window) and its capacity. */
+FEO_API int feo_comm_slot(feo_comm *comm, void **dptr, size_t *bytes);
+/* Stream-ordered barrier across the ranks (no data). */
+FEO_API int feo_comm_barrier(feo_comm *comm);
+/* Combines the `world` partials sitting in the current slots: SUM / MAX / MIN; MEAN = sum then
+ * / *divisor_host; VAR (floats) = Chan merge of [n means | n M2] partials of count_per_rank
+ * elements each, then / *divisor_host.  `out` (n elements, local) is identical on every rank. */
+FEO_API int feo_comm_allreduce(feo_comm *comm, int kind, int dtype, void *out, size_t n, size_t count_per_rank,
+                       const void *divisor_host);
+/* Tensor::{sum,mean,var,max,min} (tensor.rs:70-307) of a tensor sharded on its leading axis with
+ * axis 0 among the removed axes: `shape` is the LOCAL block, *divisor_host the counted-in-T divisor
+ * of the GLOBAL shape (feo_reduce_divisor).  Local one-pass reduction written straight into the
+ * window, then the exchange kernel; integer var runs the reference's two passes (two exchanges). */
+FEO_API int feo_reduce_sharded(feo_comm *comm, int kind, int dtype, void *out, const void *in, int rank, const size_t *shape,
+                       int naxes, const size_t *axes, const void *divisor_host);
+/* All-gather by pulling over NVLink: out = part 0 | part 1 | ...; parts[r] is rank r's buffer (feo_peer_alloc'ed
+ * there) as mapped in THIS process, each bytes_per_part long. */
+FEO_API int feo_comm_gather(feo_comm *comm, void *out, const void *const *parts, size_t bytes_per_part);
+/* DynamicMatrix::matmul (matrix.rs:76-90) with A row-sharded (this rank's [M,K] block, C likewise) and B row-sharded:
+ * b_parts[r] = rank r's [K / world, N] panel in peer-mapped memory.  f32 TF32X3: the split / transpose pre-pass pulls
+ * the panels over NVLink itself, no gathered copy of B is written; otherwise pull-gather into scratch, then the
+ * kernel.  Ends with a barrier, so a panel may be overwritten once the call has completed on its owner's stream. */
+FEO_API int feo_matmul_sharded_b(feo_comm *comm, int algo, int dtype, void *C, const void *A, const void *const *b_parts, size_t M,
+                         size_t K, size_t N);
+/* DynamicVector::vecmul (vector.rs:71-78) on identically sharded operands [batch, n_local]. */
+FEO_API int feo_dot_sharded(feo_comm *comm, int dtype, void *out, const void *a, const void *b, size_t batch, size_t n_local);
 
 #ifdef __cplusplus
 }

@@ -1,18 +1,25 @@
 #!/usr/bin/env python
 """Multi-GPU parity of the sharded path (run under torchrun, one rank per GPU, NCCL):
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sharded_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multigpu/sharded_check.py
 
 Every rank builds the same global tensors, uploads its block of leading rows, runs the sharded op through
 feotensor_b200.sharded.CudaEngine (C ABI kernels + NCCL), and compares with the same op on the whole tensor
 computed on its own GPU and with the CPU oracle: ints / max / min bit-exact, float sums within tolerance.
+
+The checks run twice: with the NCCL exchange steps and with the native peer-memory exchange kernels (csrc/peer.cu,
+`PeerComm`), whose replicated results must also be bit-identical across the ranks.
+`--same-device` puts every rank on cuda:0 with gloo as the rendezvous (a one-GPU box can then exercise the IPC windows
+and the exchange kernels; the ranks' kernels time-slice, so it is a correctness run only); NCCL is skipped there.
 """
+import argparse
+import zlib
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 
@@ -24,14 +31,40 @@ def main():
     from feotensor_b200 import sharded
     from oracle import feo_oracle as o  # checker only
 
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--same-device", action="store_true")
+    args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    if args.same_device:
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.same_device:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_stream(torch.cuda.Stream())
     ctx = feo.Context(local)
-    eng = sharded.CudaEngine(ctx)
+    comm = sharded.PeerComm(ctx)
+    total = 0
+    for label, eng in (("nccl", None if args.same_device else sharded.CudaEngine(ctx)), ("peer", sharded.CudaEngine(ctx, comm=comm))):
+        if eng is not None:
+            total += run_checks(feo, sharded, o, dist, ctx, eng, rank, world, label, with_gather=not args.same_device)
+    ctx.sync()
+    dist.barrier()
+    comm.close()
+    if rank == 0:
+        print(f"sharded_check ok: world={world}, {total} checks per rank, {ctx.launch_count()} kernel launches on rank 0", flush=True)
+    dist.destroy_process_group()
+
+
+def run_checks(feo, sharded, o, dist, ctx, eng, rank, world, label, with_gather=True):
     rng = np.random.default_rng(99)
     checks = 0
+
+    def same_on_every_rank(arr, msg):
+        crcs = [None] * world
+        dist.all_gather_object(crcs, zlib.crc32(np.ascontiguousarray(arr).tobytes()))
+        assert len(set(crcs)) == 1, f"{label} {msg}: replicated result differs across ranks {crcs}"
 
     def gen(dt, shape):
         if dt in ("f32", "f64"):
@@ -60,7 +93,8 @@ def main():
                     g, single, want = got.local.to_numpy(), rows(single), rows(want)
                 else:
                     g = got.to_numpy()
-                msg = f"{dt} {kind} {axes}"
+                    same_on_every_rank(g, f"{dt} {kind} {axes}")
+                msg = f"{label} {dt} {kind} {axes}"
                 if dt in ("i32", "i64", "u32") or kind in ("max", "min"):
                     np.testing.assert_array_equal(g, want, err_msg=msg)
                     np.testing.assert_array_equal(g, single, err_msg=msg)
@@ -71,6 +105,7 @@ def main():
                 checks += 1
         p, q = gen(dt, (R * 1000,)), gen(dt, (R * 1000,))
         got = sharded.shard_rows(eng, p).dot(sharded.shard_rows(eng, q)).to_numpy()
+        same_on_every_rank(got, f"{dt} dot")
         if dt in ("i32", "i64", "u32"):
             np.testing.assert_array_equal(got, o.dot(p, q))
         else:
@@ -80,18 +115,31 @@ def main():
         r1 = sharded.shard_rows(eng, A).matmul(feo.Tensor(feo.shape(*B.shape), B, ctx=ctx), algo="simt")
         Bs = gen(dt, (16 * world, 32))
         A2 = gen(dt, (16 * world, 16 * world))
-        r2 = sharded.shard_rows(eng, A2).matmul(sharded.shard_rows(eng, Bs), b_sharded=True, algo="simt")
-        for r, w in ((r1, want), (r2, o.matmul(A2, Bs))):
+        pairs = [(r1, want)]
+        if with_gather or label == "peer":
+            # B row-sharded: NCCL all-gather, or (peer engine) panels pulled over NVLink by the kernels themselves
+            Bsh = sharded.shard_rows(eng, Bs, peer=(label == "peer"))
+            pairs.append((sharded.shard_rows(eng, A2).matmul(Bsh, b_sharded=True, algo="simt"), o.matmul(A2, Bs)))
+        for r, w in pairs:
             if dt in ("i32", "i64", "u32"):
                 np.testing.assert_array_equal(r.local.to_numpy(), rows(w))
             else:
                 np.testing.assert_allclose(r.local.to_numpy(), rows(w), rtol=1e-4, atol=1e-5)
             checks += 1
-    ctx.sync()
-    dist.barrier()
-    if rank == 0:
-        print(f"sharded_check ok: world={world}, {checks} checks per rank, {ctx.launch_count()} kernel launches on rank 0", flush=True)
-    dist.destroy_process_group()
+    if label == "peer":
+        # f32 on the tensor cores with the gather fused into the split / transpose pre-pass (ragged N and K included)
+        for (M, K, N) in ((64 * world, 96 * world, 200), (128 * world, 32 * world, 257)):
+            A, B = gen("f32", (M, K)), gen("f32", (K, N))
+            Bsh = sharded.shard_rows(eng, B, peer=True)
+            got = sharded.shard_rows(eng, A).matmul(Bsh, b_sharded=True, algo="tf32x3").local.to_numpy()
+            exact = rows(A.astype(np.float64) @ B.astype(np.float64))
+            bound = rows(np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64))
+            err = np.abs(got - exact)
+            assert np.all(err <= np.maximum(2 * np.abs(rows(o.matmul(A, B)) - exact), 2.0 ** -20 * bound)), f"tf32x3 sharded-B {M}x{K}x{N}"
+            dist.barrier()
+            Bsh.peer.close()
+            checks += 1
+    return checks
 
 
 if __name__ == "__main__":

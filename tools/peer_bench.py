@@ -1,0 +1,143 @@
+#!/usr/bin/env python
+"""Exchange step of the sharded reductions: NCCL all-reduce / all-gather vs the native peer-memory kernels (csrc/peer.cu).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/peer_bench.py
+
+Per case: the whole sharded op (local reduction + exchange + epilogue) timed with CUDA events on the launching stream,
+`--iters` back-to-back calls after warm-up, max over ranks; rank 0 prints one JSON line per case.
+"""
+import argparse
+import json
+import os
+import sys
+
+import ctypes as C
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--big", action="store_true", help="add the config-3 sized cases (1 GiB per rank)")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+
+    import feotensor_b200 as feo
+    from feotensor_b200 import _lib as L
+    from feotensor_b200 import sharded
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = feo.Context(local)
+    comm = sharded.PeerComm(ctx)
+    engines = {"nccl": sharded.CudaEngine(ctx), "peer": sharded.CudaEngine(ctx, comm=comm)}
+
+    def timed(fn):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.iters):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e3 / args.iters], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cases = [("c1_sum_[0,2]", "f32", [64, 128, 256], "sum", [0, 2]),
+             ("c1_var_[0,2]", "f32", [64, 128, 256], "var", [0, 2]),
+             ("c1_var_i32_[0,2]", "i32", [64, 128, 256], "var", [0, 2]),
+             ("mid_sum_[0]", "f32", [8 * world, 16384, 8], "sum", [0]),
+             ("mid_max_all", "f32", [8 * world, 16384, 8], "max", [0, 1, 2])]
+    if args.big:
+        cases += [("c3_sum_[0]", "f32", [2048 * world, 16384, 8], "sum", [0]),
+                  ("c3_var_[0]", "f32", [2048 * world, 16384, 8], "var", [0]),
+                  ("c3_sum_[0,2]", "f32", [2048 * world, 16384, 8], "sum", [0, 2]),
+                  ("c3_var_all", "f32", [2048 * world, 16384, 8], "var", [0, 1, 2])]
+    for name, dt, gdims, kind, axes in cases:
+        ldims = [gdims[0] // world] + gdims[1:]
+        x = feo.Tensor.uniform(feo.Shape(ldims), 7, dtype=dt, first_index=rank * int(np.prod(ldims)), ctx=ctx) \
+            if dt == "f32" else feo.Tensor.fill(feo.Shape(ldims), rank + 1, dtype=dt, ctx=ctx)
+        res = {}
+        for label, eng in engines.items():
+            st = sharded.ShardedTensor(eng, x, gdims, rank, world)
+            res[label] = timed(lambda: st.reduce(kind, axes))
+        if kind in ("sum", "max"):
+            # the same two sequences with the Python object layer stripped: preallocated output, direct C-ABI calls
+            eng = engines["nccl"]
+            nout = int(np.prod(sharded.reduce_dims(gdims, axes)))
+            out = eng.empty([nout], x.dtype)
+            tout = eng.as_torch(out)
+            lib, code, kcode = ctx.lib, x.data.code, L.KIND_CODES[kind]
+            shp, ax, one = L.sizes(ldims), L.sizes(axes), np.ones(1, dtype=x.dtype)
+            op = dist.ReduceOp.SUM if kind == "sum" else dist.ReduceOp.MAX
+
+            def lean_nccl():
+                lib.feo_reduce_partial(ctx.handle, kcode, code, C.c_void_p(out.data.ptr), C.c_void_p(x.data.ptr), len(ldims), shp, len(axes), ax)
+                dist.all_reduce(tout, op=op)
+
+            def lean_peer():
+                lib.feo_reduce_sharded(comm.handle, kcode, code, C.c_void_p(out.data.ptr), C.c_void_p(x.data.ptr), len(ldims), shp, len(axes), ax,
+                                       one.ctypes.data_as(C.c_void_p))
+            res["lean_nccl"], res["lean_peer"] = timed(lean_nccl), timed(lean_peer)
+        if rank == 0:
+            print(json.dumps(dict({"case": name, "world": world, "local_dims": ldims, "speedup": round(res["nccl"] / res["peer"], 3)},
+                                  **{"us_" + k: round(v, 2) for k, v in res.items()})), flush=True)
+        del x
+    n_local = 1 << 20
+    p = feo.Tensor.uniform(feo.Shape([n_local]), 1, dtype="f32", first_index=rank * n_local, ctx=ctx)
+    q = feo.Tensor.uniform(feo.Shape([n_local]), 2, dtype="f32", first_index=rank * n_local, ctx=ctx)
+    res = {}
+    for label, eng in engines.items():
+        sp = sharded.ShardedTensor(eng, p, [n_local * world], rank, world)
+        sq = sharded.ShardedTensor(eng, q, [n_local * world], rank, world)
+        res[label] = timed(lambda: sp.dot(sq))
+    if rank == 0:
+        print(json.dumps({"case": "dot_1Mi_per_rank", "world": world, "us_nccl": round(res["nccl"], 2), "us_peer": round(res["peer"], 2),
+                          "speedup": round(res["nccl"] / res["peer"], 3)}), flush=True)
+    if args.big:
+        # config 4 row-sharded with B row-sharded too: NCCL all-gather of B + matmul vs the gather fused into the pre-pass
+        n = 8192
+        rows_ = n // world
+        A = feo.Tensor.uniform(feo.Shape([rows_, n]), 11, dtype="f32", first_index=rank * rows_ * n, ctx=ctx)
+        buf = sharded.PeerBuffer(ctx, rows_ * n * 4)
+        Bl = buf.tensor([rows_, n], "f32")
+        ctx.check(ctx.lib.feo_fill_uniform(ctx.handle, Bl.data.code, C.c_void_p(Bl.data.ptr), rows_ * n, 12, rank * rows_ * n, -1.0, 1.0))
+        res = {}
+        for label, eng in engines.items():
+            sa = sharded.ShardedTensor(eng, A, [n, n], rank, world)
+            sb = sharded.ShardedTensor(eng, Bl, [n, n], rank, world)
+            if label == "peer":
+                sb.peer = buf
+            res[label] = timed(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
+        Bfull = feo.Tensor.uniform(feo.Shape([n, n]), 12, dtype="f32", ctx=ctx)
+        sa = sharded.ShardedTensor(engines["nccl"], A, [n, n], rank, world)
+        res["replicated_b"] = timed(lambda: sa.matmul(Bfull, algo="tf32x3"))
+        if rank == 0:
+            flop = 2.0 * n * n * n
+            print(json.dumps(dict({"case": "c4_matmul_8192_b_sharded", "world": world, "speedup": round(res["nccl"] / res["peer"], 3),
+                                   "tflops_peer_whole_job": round(flop / res["peer"] / 1e6, 1),
+                                   "tflops_nccl_whole_job": round(flop / res["nccl"] / 1e6, 1)},
+                                  **{"us_" + k: round(v, 1) for k, v in res.items()})), flush=True)
+        dist.barrier()
+        buf.close()
+    ctx.sync()
+    dist.barrier()
+    comm.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
