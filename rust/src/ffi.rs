@@ -7,6 +7,13 @@ pub struct feo_ctx {
     _private: [u8; 0],
 }
 
+#[repr(C)]
+pub struct feo_comm {
+    _private: [u8; 0],
+}
+pub const FEO_MAX_PEERS: usize = 8;
+pub const FEO_PEER_HANDLE_BYTES: usize = 64;
+
 pub const FEO_OK: c_int = 0;
 pub const FEO_ERR_SHAPE: c_int = 1;
 pub const FEO_ERR_CUDA: c_int = 2;
@@ -58,4 +65,21 @@ extern "C" {
     pub fn feo_matvec(ctx: *mut feo_ctx, dtype: c_int, out: *mut c_void, a: *const c_void, v: *const c_void, m: usize, k: usize) -> c_int;
     pub fn feo_vecmat(ctx: *mut feo_ctx, dtype: c_int, out: *mut c_void, v: *const c_void, a: *const c_void, k: usize, n: usize) -> c_int;
     pub fn feo_matmul(ctx: *mut feo_ctx, algo: c_int, dtype: c_int, c: *mut c_void, a: *const c_void, b: *const c_void, m: usize, k: usize, n: usize) -> c_int;
+    pub fn feo_trim(ctx: *mut feo_ctx) -> c_int;
+
+    // Cross-GPU epilogues over peer memory (one process per GPU; the handles travel through the host's own rendezvous).
+    pub fn feo_peer_alloc(ctx: *mut feo_ctx, bytes: usize, dptr: *mut *mut c_void) -> c_int;
+    pub fn feo_peer_free(ctx: *mut feo_ctx, dptr: *mut c_void) -> c_int;
+    pub fn feo_peer_export(ctx: *mut feo_ctx, dptr: *mut c_void, handle: *mut u8) -> c_int;
+    pub fn feo_peer_open(ctx: *mut feo_ctx, handle: *const u8, dptr: *mut *mut c_void) -> c_int;
+    pub fn feo_peer_close(ctx: *mut feo_ctx, dptr: *mut c_void) -> c_int;
+    pub fn feo_comm_create(ctx: *mut feo_ctx, rank: c_int, world: c_int, windows: *const *mut c_void, window_bytes: usize, comm: *mut *mut feo_comm) -> c_int;
+    pub fn feo_comm_destroy(comm: *mut feo_comm) -> c_int;
+    pub fn feo_comm_slot(comm: *mut feo_comm, dptr: *mut *mut c_void, bytes: *mut usize) -> c_int;
+    pub fn feo_comm_barrier(comm: *mut feo_comm) -> c_int;
+    pub fn feo_comm_allreduce(comm: *mut feo_comm, kind: c_int, dtype: c_int, out: *mut c_void, n: usize, count_per_rank: usize, divisor_host: *const c_void) -> c_int;
+    pub fn feo_comm_gather(comm: *mut feo_comm, out: *mut c_void, parts: *const *const c_void, bytes_per_part: usize) -> c_int;
+    pub fn feo_reduce_sharded(comm: *mut feo_comm, kind: c_int, dtype: c_int, out: *mut c_void, input: *const c_void, rank: c_int, shape: *const usize, naxes: c_int, axes: *const usize, divisor_host: *const c_void) -> c_int;
+    pub fn feo_dot_sharded(comm: *mut feo_comm, dtype: c_int, out: *mut c_void, a: *const c_void, b: *const c_void, batch: usize, n_local: usize) -> c_int;
+    pub fn feo_matmul_sharded_b(comm: *mut feo_comm, algo: c_int, dtype: c_int, c: *mut c_void, a: *const c_void, b_parts: *const *const c_void, m: usize, k: usize, n: usize) -> c_int;
 }
