@@ -264,6 +264,87 @@ def run_suite(torch, feo, L, ctx, hbm_peak, tf_peak):
     return suite
 
 
+def run_suite_sharded(torch, dist, feo, ctx, rank, world, hbm_peak, iters=10):
+    """The configs that need an exchange, sharded on the leading axis over `world` GPUs (strong scaling of the BASELINE
+    shapes): local kernels + the library's own peer-memory exchange kernels (csrc/peer.cu).  Whole-job figures, timed
+    with CUDA events on the launching stream, max over ranks."""
+    import numpy as np
+
+    from feotensor_b200 import sharded
+    comm = sharded.PeerComm(ctx)
+    eng = sharded.CudaEngine(ctx, comm=comm)
+    stream = torch.cuda.current_stream()
+    out = {}
+
+    def timed_ms(fn, n=iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # C3 [16384,16384,8] f32, rows split over the ranks
+    g3 = [16384, 16384, 8]
+    l3 = [g3[0] // world] + g3[1:]
+    n_local = int(np.prod(l3))
+    x = feo.Tensor.uniform(feo.Shape(l3), SEED + 4, dtype="f32", first_index=rank * n_local, ctx=ctx)
+    sx = sharded.ShardedTensor(eng, x, g3, rank, world)
+    for axes in ([0], [2], [0, 2], [1, 2], [0, 1, 2]):
+        nout = int(np.prod(sharded.reduce_dims(g3, axes)))
+        for kind in ("sum", "var", "max"):
+            ms = timed_ms(lambda: sx.reduce(kind, axes))
+            gbs = 4.0 * (world * n_local + nout) / ms / 1e6
+            out[f"C3_{kind}_axes{''.join(map(str, axes))}"] = {"ms": round(ms, 4), "GB/s": round(gbs, 1), "frac_hbm_per_gpu": round(gbs / world / hbm_peak, 3),
+                                                             "exchange": 0 in axes}
+    del sx, x
+    # C1 [64,128,256]: latency of local reduction + exchange + epilogue
+    if 64 % world == 0:
+        g1 = [64, 128, 256]
+        l1 = [64 // world, 128, 256]
+        x = feo.Tensor.uniform(feo.Shape(l1), SEED + 5, dtype="f32", first_index=rank * int(np.prod(l1)), ctx=ctx)
+        sx = sharded.ShardedTensor(eng, x, g1, rank, world)
+        for kind in ("sum", "mean", "var"):
+            out[f"C1_{kind}_axes02_us"] = round(timed_ms(lambda: sx.reduce(kind, [0, 2]), 50) * 1e3, 2)
+        del sx, x
+    # C5 dot on 1e9 elements, both vectors split
+    nd = 1_000_000_000 // world
+    p_ = feo.Tensor.uniform(feo.Shape([nd]), SEED + 6, dtype="f32", first_index=rank * nd, ctx=ctx)
+    q_ = feo.Tensor.uniform(feo.Shape([nd]), SEED + 7, dtype="f32", first_index=rank * nd, ctx=ctx)
+    sp, sq = sharded.ShardedTensor(eng, p_, [nd * world], rank, world), sharded.ShardedTensor(eng, q_, [nd * world], rank, world)
+    ms = timed_ms(lambda: sp.dot(sq))
+    out["C5_dot_1e9"] = {"ms": round(ms, 4), "GB/s": round(8.0 * nd * world / ms / 1e6, 1), "frac_hbm_per_gpu": round(8.0 * nd / ms / 1e6 / hbm_peak, 3)}
+    del sp, sq, p_, q_
+    # C4 8192^3, A (and C) row-sharded; B replicated, or row-sharded with the gather fused into the 3xTF32 pre-pass
+    n = 8192
+    rows_ = n // world
+    A = feo.Tensor.uniform(feo.Shape([rows_, n]), SEED + 8, dtype="f32", first_index=rank * rows_ * n, ctx=ctx)
+    buf = sharded.PeerBuffer(ctx, rows_ * n * 4)
+    Bl = buf.tensor([rows_, n], "f32")
+    ctx.check(ctx.lib.feo_fill_uniform(ctx.handle, Bl.data.code, C.c_void_p(Bl.data.ptr), rows_ * n, SEED + 9, rank * rows_ * n, -1.0, 1.0))
+    Bfull = feo.Tensor.uniform(feo.Shape([n, n]), SEED + 9, dtype="f32", ctx=ctx)
+    sa = sharded.ShardedTensor(eng, A, [n, n], rank, world)
+    sb = sharded.ShardedTensor(eng, Bl, [n, n], rank, world)
+    sb.peer = buf
+    flop = 2.0 * n * n * n
+    for label, fn in (("b_replicated", lambda: sa.matmul(Bfull, algo="tf32x3")), ("b_sharded_fused_gather", lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))):
+        ms = timed_ms(fn)
+        out[f"C4_matmul_tf32x3_{label}"] = {"ms": round(ms, 4), "TFLOP/s": round(flop / ms / 1e9, 1)}
+    dist.barrier()
+    del sa, sb, Bl, A, Bfull
+    buf.close()
+    comm.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -433,6 +514,12 @@ def main():
             line["suite"] = run_suite(torch, feo, L, ctx, hbm_peak, tf_peak)
         except Exception as e:  # the headline line must still be printed
             line["suite"] = {"error": repr(e)}
+    if world > 1 and not args.no_suite:
+        try:
+            sharded_suite = run_suite_sharded(torch, dist, feo, ctx, rank, world, hbm_peak)
+        except Exception as e:  # collective code: every rank runs it; the headline line must still be printed
+            sharded_suite = {"error": repr(e)}
+        line["suite_sharded"] = sharded_suite
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import feo_oracle as oracle  # checker / baseline only: never on the measured GPU path
         oracle.lib()

@@ -40,6 +40,16 @@ cudaError_t feo_alloc_async(feo_ctx *ctx, void **ptr, size_t bytes) {
     return cudaMallocAsync(ptr, bytes, ctx->stream);
 }
 
+int feo_side_stream(feo_ctx *ctx) {
+    if (ctx->side_stream) return FEO_OK;
+    int lo = 0, hi = 0;
+    FEO_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    FEO_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
+    FEO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    FEO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    return FEO_OK;
+}
+
 int feo_workspace(feo_ctx *ctx, size_t bytes, void **ptr) {
     if (bytes > ctx->workspace_bytes) {
         if (ctx->workspace) FEO_CUDA(ctx, cudaFreeAsync(ctx->workspace, ctx->stream));
@@ -118,6 +128,9 @@ int feo_shutdown(feo_ctx *ctx) {
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->arith_flag) cudaFree(ctx->arith_flag);
     if (ctx->counters) cudaFree(ctx->counters);
+    if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return FEO_OK;

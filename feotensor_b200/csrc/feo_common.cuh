@@ -22,7 +22,8 @@ enum feo_knob {
     FEO_KNOB_PDL = 5,           // programmatic dependent launch of independent back-to-back broadcast kernels: 0 = on, 1 = off
     FEO_KNOB_BCAST_L2KEEP = 6,  // L2 evict_last policy on broadcast operands: 0 = on, 1 = off
     FEO_KNOB_REDUCE_FUSE = 7,   // split reductions: last-arriving CTA combines the partials in the same launch: 0 = auto (small inputs), 1 = off, 2 = always
-    FEO_KNOB_COUNT = 8
+    FEO_KNOB_GATHER_OVERLAP = 8,  // sharded-B matmul: pull B's panels on a side stream while the matmul kernel runs: 0 = on, 1 = off
+    FEO_KNOB_COUNT = 9
 };
 
 // Address ranges of a launch, for the hazard check that lets independent back-to-back kernels overlap their tails.
@@ -34,6 +35,8 @@ struct feo_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;      // stream in use
     cudaStream_t own_stream = nullptr;  // stream created by feo_init
+    cudaStream_t side_stream = nullptr;  // high-priority helper stream (created on first use, see feo_side_stream)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaMemPool_t pool = nullptr;       // this context's own stream-ordered pool (never trimmed at synchronisation)
     void *workspace = nullptr;          // scratch for two-stage reductions
     size_t workspace_bytes = 0;
@@ -56,6 +59,8 @@ int feo_workspace(feo_ctx *ctx, size_t bytes, void **ptr);
 // Stream-ordered allocation from the context's own pool.  A private pool means a block freed on another context's stream
 // is never handed out here with a hidden cross-stream dependency -- which would deadlock kernels that wait for peers.
 cudaError_t feo_alloc_async(feo_ctx *ctx, void **ptr, size_t bytes);
+// Creates ctx->side_stream / ev_fork / ev_join on first use.
+int feo_side_stream(feo_ctx *ctx);
 
 #define FEO_CUDA(ctx, expr)                                                                       \
     do {                                                                                          \

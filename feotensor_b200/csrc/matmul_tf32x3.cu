@@ -108,7 +108,11 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 __global__ void __launch_bounds__(kThreads, 1)
 matmul_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                     float *__restrict__ C, int M, int N, int num_k_blocks, int kc) {
+                     float *__restrict__ C, int M, int N, int num_k_blocks, int kc, const unsigned int *__restrict__ ready,
+                     unsigned int ready_need, int kb_rot) {
+    // `ready` != nullptr: Bt's k-blocks are still being produced by the gathering pre-pass running concurrently on another
+    // stream; ready[kb] counts its finished CTAs (ready_need per k-block).  Iteration i works on k-block (i + kb_rot) % n,
+    // the order the pre-pass fills them in (the local panel first, then the peers' in ring order).
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
@@ -150,11 +154,37 @@ matmul_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer =====
-            for (int kb = 0; kb < num_k_blocks; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
+    if (warp == 0) {  // ===== TMA producer (lane 0 issues; the whole warp looks ahead on the readiness flags) =====
+        int ready_upto = ready ? 0 : num_k_blocks;  // iterations [0, ready_upto) are known to be complete
+        for (int it = 0; it < num_k_blocks; ++it) {
+            if (it >= ready_upto) {
+                // every lane polls the flag of iteration it + lane; the contiguous ready prefix advances the watermark
+                const unsigned long long t0 = feo_peer::global_ns();
+                for (;;) {
+                    bool ok = false;
+                    if (it + lane < num_k_blocks) {
+                        int kbl = it + lane + kb_rot;
+                        if (kbl >= num_k_blocks) kbl -= num_k_blocks;
+                        unsigned int v;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ready + kbl) : "memory");
+                        ok = v >= ready_need;
+                    }
+                    const unsigned int mask = __ballot_sync(0xffffffffu, ok);
+                    const int prefix = __ffs(~mask) - 1;  // number of leading ready iterations (32 if all)
+                    if (prefix != 0) { ready_upto = it + (prefix < 0 ? 32 : prefix); break; }
+                    if (feo_peer::global_ns() - t0 > 10ull * 1000 * 1000 * 1000) {
+                        if (lane == 0) printf("matmul_tf32x3: k-block %d of B never arrived (block %d)\n", it, blockIdx.x);
+                        __trap();
+                    }
+                    __nanosleep(100);
+                }
+                asm volatile("fence.proxy.async;" ::: "memory");  // the pre-pass wrote through the generic proxy; TMA reads through the async one
+            }
+            if (lane == 0) {
+                int kb = it + kb_rot;
+                if (kb >= num_k_blocks) kb -= num_k_blocks;
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1, 0);
                 uint8_t *st = smem + s * kStageBytes;
                 mbar_expect_tx(&full_bar[s], kStageBytes);
@@ -163,6 +193,7 @@ matmul_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 tma_load_2d(st + 2 * kTileABytes, &map_b_hi, &full_bar[s], kb * BK, n0);
                 tma_load_2d(st + 2 * kTileABytes + kTileBBytes, &map_b_lo, &full_bar[s], kb * BK, n0);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ===== MMA issuer =====
@@ -300,13 +331,20 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(float *__restrict_
 // Tile = 32 k-rows x 128 n-columns; every lane loads 16 bytes along n (512 contiguous bytes per warp request, all four of
 // a thread's requests in flight before the first use) and stores 16 bytes along k.
 constexpr int GT_K = 32, GT_N = 128;
-__global__ void __launch_bounds__(256) split_transpose_gather_kernel(float *__restrict__ hi, float *__restrict__ lo,
-                                                                     const __grid_constant__ feo_peer::BParts parts,
-                                                                     const __grid_constant__ feo_peer::XchgParams sync, int K, int N, int Kp,
-                                                                     bool vec) {
+// k-blocks are produced in rotated order (blockIdx.y = 0 is the first k-block of THIS rank's own panel, then the peers' in
+// ring order): every rank pulls from a different owner at any time, instead of all eight draining one GPU's links.
+// `ready` (optional): ready[k-block] += 1 when a CTA has published its tile -- the matmul kernel, already running on the
+// main stream, waits on these per k-block, so the NVLink pull overlaps the tensor-core work on the panels already here.
+// (<= 42 registers so that these CTAs fit on an SM beside one 168-register matmul CTA.)
+__global__ void __launch_bounds__(256, 6) split_transpose_gather_kernel(float *__restrict__ hi, float *__restrict__ lo,
+                                                                        const __grid_constant__ feo_peer::BParts parts,
+                                                                        const __grid_constant__ feo_peer::XchgParams sync, int K, int N, int Kp,
+                                                                        bool vec, int kb_rot, unsigned int *__restrict__ ready) {
     __shared__ float tile[GT_K][GT_N + 1];
     feo_peer::signal_and_wait(sync);
-    const int k0 = blockIdx.y * GT_K, n0 = blockIdx.x * GT_N;
+    int kblock = blockIdx.y + kb_rot;
+    if (kblock >= (int)gridDim.y) kblock -= gridDim.y;
+    const int k0 = kblock * GT_K, n0 = blockIdx.x * GT_N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 v[4];
 #pragma unroll
@@ -346,6 +384,12 @@ __global__ void __launch_bounds__(256) split_transpose_gather_kernel(float *__re
             *reinterpret_cast<float4 *>(hi + o) = h;
             *reinterpret_cast<float4 *>(lo + o) = l;
         }
+    }
+    if (ready) {
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(ready + kblock, 1u);
     }
 }
 
@@ -399,23 +443,45 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
     const size_t Kp = (K + BK - 1) / BK * BK;
     void *ws = nullptr;
     const size_t a_elems = M * Kp, b_elems = N * Kp;
-    int rc = feo_workspace(ctx, (2 * a_elems + 2 * b_elems) * sizeof(float), &ws);
+    int rc = feo_workspace(ctx, (2 * a_elems + 2 * b_elems) * sizeof(float) + (Kp / BK) * sizeof(unsigned int), &ws);
     if (rc != FEO_OK) return rc;
     float *a_hi = (float *)ws, *a_lo = a_hi + a_elems, *b_hi = a_lo + a_elems, *b_lo = b_hi + b_elems;
+    const int num_kb = (int)(Kp / BK);
+    static_assert(GT_K == BK, "one gather tile row = one k-block of the main kernel");
+
+    // B arriving from peers: the pre-pass goes to a high-priority side stream and the main kernel consumes k-blocks as
+    // they are published (knob FEO_KNOB_GATHER_OVERLAP = 1: plain stream order instead)
+    unsigned int *ready = nullptr;
+    int kb_rot = 0;
+    bool overlap = false;
+    if (parts) {
+        kb_rot = (int)(((size_t)sync->rank * parts->rows_per_part) / BK);
+        overlap = ctx->knobs[FEO_KNOB_GATHER_OVERLAP] != 1 && feo_side_stream(ctx) == FEO_OK;
+        bool vec = N % 4 == 0;
+        for (int r = 0; r < parts->world; ++r) vec = vec && feo_aligned16(parts->part[r]);
+        const dim3 ggrid((unsigned)feo_ceil_div(N, (size_t)GT_N), (unsigned)num_kb);
+        if (overlap) {
+            ready = reinterpret_cast<unsigned int *>(b_lo + b_elems);
+            FEO_CUDA(ctx, cudaMemsetAsync(ready, 0, (size_t)num_kb * sizeof(unsigned int), ctx->stream));
+            FEO_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+            FEO_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+            split_transpose_gather_kernel<<<ggrid, 256, 0, ctx->side_stream>>>(b_hi, b_lo, *parts, *sync, (int)K, (int)N, (int)Kp, vec, kb_rot, ready);
+            FEO_LAUNCH_CHECK(ctx);
+            FEO_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+        } else {
+            split_transpose_gather_kernel<<<ggrid, 256, 0, ctx->stream>>>(b_hi, b_lo, *parts, *sync, (int)K, (int)N, (int)Kp, vec, kb_rot, nullptr);
+            FEO_LAUNCH_CHECK(ctx);
+        }
+    }
 
     size_t blocks = feo_ceil_div(a_elems / 4, (size_t)256);
     if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
     split_rows_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a_hi, a_lo, (const float *)A, (int)M, (int)K, (int)Kp, K % 4 == 0);
     FEO_LAUNCH_CHECK(ctx);
-    if (parts) {
-        bool vec = N % 4 == 0;
-        for (int r = 0; r < parts->world; ++r) vec = vec && feo_aligned16(parts->part[r]);
-        split_transpose_gather_kernel<<<dim3((unsigned)feo_ceil_div(N, (size_t)GT_N), (unsigned)(Kp / GT_K)), 256, 0, ctx->stream>>>(
-            b_hi, b_lo, *parts, *sync, (int)K, (int)N, (int)Kp, vec);
-    } else {
+    if (!parts) {
         split_transpose_kernel<<<dim3((unsigned)feo_ceil_div(N, (size_t)32), (unsigned)(Kp / 32)), 256, 0, ctx->stream>>>(b_hi, b_lo, (const float *)B, (int)K, (int)N, (int)Kp);
+        FEO_LAUNCH_CHECK(ctx);
     }
-    FEO_LAUNCH_CHECK(ctx);
 
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     if (!make_map(&ma_hi, a_hi, M, Kp, BM) || !make_map(&ma_lo, a_lo, M, Kp, BM) || !make_map(&mb_hi, b_hi, N, Kp, BN) ||
@@ -426,8 +492,10 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
     const dim3 grid((unsigned)tiles);
     int kc = ctx->knobs[FEO_KNOB_MATMUL_TF32_KC];
     if (kc <= 0) kc = 2;  // k-blocks per TMEM accumulation chain (24 truncating accumulates), see the file header
-    matmul_tf32x3_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, (float *)C, (int)M, (int)N, (int)(Kp / BK), kc);
+    matmul_tf32x3_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, (float *)C, (int)M, (int)N, num_kb, kc, ready,
+                                                                      (unsigned)feo_ceil_div(N, (size_t)GT_N), kb_rot);
     FEO_LAUNCH_CHECK(ctx);
+    if (overlap) FEO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // the workspace is reused by the next call
     return FEO_OK;
 }
 

@@ -623,24 +623,48 @@ __global__ void __launch_bounds__(kThreads) reduce_generic_kernel(T *__restrict_
     }
 }
 
-// ---- stage 2: merge S partial accumulators per output, in split order ------------------------------------------
-template <typename T, int KIND, bool WARP>
+// ---- stage 2: merge S partial accumulators per output, in a fixed order (deterministic) -------------------------
+// MODE 0: a thread per output (many outputs); 1: a warp per output; 2: a CTA per output (few outputs, thousands of splits:
+// a full reduction of 1 GiB leaves ~4700 partials, which one warp merged in ~100 us).  Warp / CTA: every lane takes a
+// contiguous run of splits, loads them in batches, then the shuffle tree (and, per CTA, the 8 warp results in order).
+template <typename T, int KIND, int MODE>
 __global__ void __launch_bounds__(kThreads) reduce_stage2_kernel(T *__restrict__ out, const void *__restrict__ partial,
                                                                  long long nout, long long S, int fin, T divisor, int *flag) {
     const Acc<T, KIND> *p = reinterpret_cast<const Acc<T, KIND> *>(partial);
-    if constexpr (WARP) {
-        const long long o = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
-        const int lane = threadIdx.x & 31;
+    if constexpr (MODE >= 1) {
+        constexpr int LANES = MODE == 1 ? 32 : kThreads;
+        const long long o = MODE == 1 ? ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5 : (long long)blockIdx.x;
+        const int lane = MODE == 1 ? (threadIdx.x & 31) : threadIdx.x;
         if (o >= nout) return;
         Acc<T, KIND> acc;
         acc.init((T)0);
         if constexpr (KIND == K_SQDEV) acc.m = p[o].m;
-        // each lane takes a contiguous run of splits; the order is fixed, so results are deterministic
-        const long long per = (S + 31) / 32;
+        const long long per = (S + LANES - 1) / LANES;
         const long long lo = lane * per, hi = (lo + per < S) ? lo + per : S;
-        for (long long s = lo; s < hi; ++s) acc.merge(p[s * nout + o]);
+        constexpr int B = 4;
+        for (long long s = lo; s < hi; s += B) {
+            Acc<T, KIND> buf[B];
+#pragma unroll
+            for (int i = 0; i < B; ++i)
+                if (s + i < hi) buf[i] = p[(s + i) * nout + o];
+#pragma unroll
+            for (int i = 0; i < B; ++i)
+                if (s + i < hi) acc.merge(buf[i]);
+        }
         warp_merge(acc);
-        if (lane == 0) finalize(acc, out, o, nout, fin, divisor, flag);
+        if constexpr (MODE == 1) {
+            if (lane == 0) finalize(acc, out, o, nout, fin, divisor, flag);
+        } else {
+            __shared__ Acc<T, KIND> smem[kThreads / 32];
+            if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = acc;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                Acc<T, KIND> t = smem[0];
+#pragma unroll
+                for (int w = 1; w < kThreads / 32; ++w) t.merge(smem[w]);
+                finalize(t, out, o, nout, fin, divisor, flag);
+            }
+        }
     } else {
         const long long o = (long long)blockIdx.x * kThreads + threadIdx.x;
         if (o >= nout) return;
@@ -797,12 +821,14 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
     }
     FEO_LAUNCH_CHECK(ctx);
     if (G.S > 1 && !G.counters) {
-        if (G.nout < 4096) {
+        if (G.nout <= 64 && G.S >= 256) {
+            reduce_stage2_kernel<T, KIND, 2><<<(unsigned)G.nout, kThreads, 0, ctx->stream>>>(out, partial, G.nout, G.S, fin, divisor, flag);
+        } else if (G.nout < 4096) {
             const long long blocks = feo_ceil_div((size_t)G.nout * 32, (size_t)kThreads);
-            reduce_stage2_kernel<T, KIND, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, G.nout, G.S, fin, divisor, flag);
+            reduce_stage2_kernel<T, KIND, 1><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, G.nout, G.S, fin, divisor, flag);
         } else {
             const long long blocks = feo_ceil_div((size_t)G.nout, (size_t)kThreads);
-            reduce_stage2_kernel<T, KIND, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, G.nout, G.S, fin, divisor, flag);
+            reduce_stage2_kernel<T, KIND, 0><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, G.nout, G.S, fin, divisor, flag);
         }
         FEO_LAUNCH_CHECK(ctx);
     }

@@ -70,6 +70,7 @@ class PeerComm:
         h = C.c_void_p()
         ctx.check(self.lib.feo_comm_create(ctx.handle, self.rank, self.world, arr, self.window_bytes, C.byref(h)))
         self.handle = h
+        self.slot_bytes = self.slot()[1]
 
     def slot(self):
         p, n = C.c_void_p(), C.c_size_t()
@@ -291,6 +292,7 @@ class ShardedTensor:
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
+        self._plans = {}  # (kind, axes) -> validated shapes / divisor, so repeated reductions skip the host bookkeeping
         if self.global_dims[0] % self.world != 0:
             raise ValueError(f"leading extent {self.global_dims[0]} is not divisible by {self.world} ranks")
         want = [self.global_dims[0] // self.world] + self.global_dims[1:]
@@ -355,19 +357,21 @@ class ShardedTensor:
         Returns a ShardedTensor when the leading axis is kept, else a replicated array (identical on every rank)."""
         eng, dist = self.engine, _dist()
         axes = [int(a) for a in axes]
-        out_dims = reduce_dims(self.global_dims, axes)  # validates the axes like the reference would panic
+        plan = self._plans.get((kind, tuple(axes)))
+        if plan is None:
+            out_dims = reduce_dims(self.global_dims, axes)  # validates the axes like the reference would panic
+            dtype = np.dtype(eng.dtype(self.local))
+            plan = (out_dims, int(np.prod(out_dims)), dtype, axes if axes else list(range(len(self.global_dims))),
+                    reduce_divisor(dtype, self.global_dims, axes))
+            self._plans[(kind, tuple(axes))] = plan
+        out_dims, nout, dtype, local_axes, n_div = plan  # axes == [] reduces everything (tensor.rs:84): per shard, all local axes
         if axes and 0 not in axes:
             out_local = eng.reduce(kind, self.local, axes)
             return self._like(out_local, out_dims)
-        nout = int(np.prod(out_dims))
-        dtype = np.dtype(eng.dtype(self.local))
-        # axes == [] reduces everything (tensor.rs:84); per shard that is "all local axes"
-        local_axes = axes if axes else list(range(len(self.global_dims)))
-        n_div = reduce_divisor(dtype, self.global_dims, axes)
         is_float = dtype.kind == "f"
         comm = getattr(eng, "comm", None)
         if comm is not None and kind in ("sum", "mean", "var", "max", "min") and \
-                nout * dtype.itemsize * (2 if kind == "var" and is_float else 1) <= comm.slot()[1]:
+                nout * dtype.itemsize * (2 if kind == "var" and is_float else 1) <= comm.slot_bytes:
             return eng.reshape(eng.reduce_sharded(kind, self.local, local_axes, nout, n_div), out_dims)
 
         def allreduce(t, op):

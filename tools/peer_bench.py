@@ -122,6 +122,10 @@ def main():
             if label == "peer":
                 sb.peer = buf
             res[label] = timed(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
+            if label == "peer":
+                ctx.tune(L.KNOB_GATHER_OVERLAP, 1)
+                res["peer_no_overlap"] = timed(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
+                ctx.tune(L.KNOB_GATHER_OVERLAP, 0)
         Bfull = feo.Tensor.uniform(feo.Shape([n, n]), 12, dtype="f32", ctx=ctx)
         sa = sharded.ShardedTensor(engines["nccl"], A, [n, n], rank, world)
         res["replicated_b"] = timed(lambda: sa.matmul(Bfull, algo="tf32x3"))
