@@ -384,6 +384,134 @@ int launch_generic(feo_ctx *ctx, T *out, const T *a, const T *b, const Collapsed
     return FEO_OK;
 }
 
+// ---- any shape, any strides: work in the FLAT index space of the dense output -----------------------------------------
+// The vector planner needs the inner extent to be a multiple of the vector; [n, 3] * [3] or an outer product with 4099
+// columns fell to one element per thread with 64-bit div/mod.  The output is dense whatever the operands look like, so a
+// thread owns 4 consecutive flat outputs (one 16-byte store); operand offsets are decoded once per vector with 32-bit
+// magic-number division, the other three elements step along the inner dim and re-decode only across a row end.
+// Operand loads go through L1 (small broadcast operands live there; a dense operand's four scalar loads coalesce).
+struct FastDiv {
+    unsigned int d, mul, shift;
+};
+inline FastDiv make_fastdiv(unsigned int d) {
+    FastDiv f;
+    f.d = d;
+    unsigned int sh = 0;
+    while (sh < 32 && (1ull << sh) < d) ++sh;
+    f.shift = sh;
+    f.mul = (unsigned int)((((1ull << 32) * ((1ull << sh) - d)) / d) + 1);
+    return f;
+}
+__device__ __forceinline__ unsigned int fd_div(unsigned int n, const FastDiv &f) { return (__umulhi(n, f.mul) + n) >> f.shift; }
+
+template <int RANK> struct FlatParams {
+    FastDiv ext[RANK];
+    unsigned int sa[RANK], sb[RANK];
+    unsigned int n;
+};
+
+template <int RANK> __device__ __forceinline__ void flat_decode(unsigned int i, const FlatParams<RANK> &P, unsigned int &oa, unsigned int &ob,
+                                                               unsigned int &inner) {
+    oa = 0; ob = 0;
+    unsigned int rem = i;
+#pragma unroll
+    for (int d = RANK - 1; d >= 1; --d) {
+        const unsigned int q = fd_div(rem, P.ext[d]);
+        const unsigned int c = rem - q * P.ext[d].d;
+        if (d == RANK - 1) inner = c;
+        oa += c * P.sa[d]; ob += c * P.sb[d];
+        rem = q;
+    }
+    if (RANK == 1) inner = rem;
+    oa += rem * P.sa[0]; ob += rem * P.sb[0];
+}
+
+template <typename T, int OP, int RANK>
+__global__ void __launch_bounds__(kThreads) bcast_flat_kernel(T *__restrict__ out, const T *__restrict__ a, const T *__restrict__ b,
+                                                              const __grid_constant__ FlatParams<RANK> P, int *flag) {
+    constexpr int VN = VecN<T>::value;
+    using V = AVec<T, VN>;
+    const unsigned int nvec = P.n / VN;
+    const unsigned int ext_in = P.ext[RANK - 1].d, sa_in = P.sa[RANK - 1], sb_in = P.sb[RANK - 1];
+    for (unsigned int v = blockIdx.x * kThreads + threadIdx.x; v < nvec; v += gridDim.x * kThreads) {
+        const unsigned int i0 = v * VN;
+        unsigned int oa, ob, inner;
+        flat_decode<RANK>(i0, P, oa, ob, inner);
+        T x[VN], y[VN];
+        if (inner + VN <= ext_in) {  // the whole vector sits in one row
+            if (sa_in == 1 && (reinterpret_cast<uintptr_t>(a + oa) & 15u) == 0) {
+                const V t = *reinterpret_cast<const V *>(a + oa);
+#pragma unroll
+                for (int k = 0; k < VN; ++k) x[k] = t.v[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < VN; ++k) x[k] = __ldg(a + oa + k * sa_in);
+            }
+            if (sb_in == 1 && (reinterpret_cast<uintptr_t>(b + ob) & 15u) == 0) {
+                const V t = *reinterpret_cast<const V *>(b + ob);
+#pragma unroll
+                for (int k = 0; k < VN; ++k) y[k] = t.v[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < VN; ++k) y[k] = __ldg(b + ob + k * sb_in);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < VN; ++k) {
+                unsigned int ka = oa + k * sa_in, kb = ob + k * sb_in, dummy;
+                if (inner + k >= ext_in) flat_decode<RANK>(i0 + k, P, ka, kb, dummy);
+                x[k] = __ldg(a + ka); y[k] = __ldg(b + kb);
+            }
+        }
+        V r;
+#pragma unroll
+        for (int k = 0; k < VN; ++k) r.v[k] = apply_op<OP>(x[k], y[k], flag);
+        st_stream(reinterpret_cast<V *>(out + i0), r);
+    }
+    // the last n % VN elements
+    if (blockIdx.x == 0 && threadIdx.x < P.n - nvec * VN) {
+        const unsigned int i = nvec * VN + threadIdx.x;
+        unsigned int oa, ob, inner;
+        flat_decode<RANK>(i, P, oa, ob, inner);
+        out[i] = apply_op<OP>(__ldg(a + oa), __ldg(b + ob), flag);
+    }
+}
+
+// Returns -1 when the shape does not fit the 32-bit flat path (more than 4 collapsed dims, >= 2^31 elements or offsets).
+template <typename T, int OP, int RANK>
+int launch_flat_bcast_rank(feo_ctx *ctx, T *out, const T *a, const T *b, const Collapsed &c) {
+    FlatParams<RANK> P;
+    long long n = 1;
+    for (int d = 0; d < RANK; ++d) {
+        P.ext[d] = make_fastdiv((unsigned int)c.ext[d]);
+        P.sa[d] = (unsigned int)c.sa[d]; P.sb[d] = (unsigned int)c.sb[d];
+        n *= c.ext[d];
+    }
+    P.n = (unsigned int)n;
+    constexpr int VN = VecN<T>::value;
+    long long blocks = (n / VN + kThreads - 1) / kThreads;
+    const long long cap = (long long)ctx->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    bcast_flat_kernel<T, OP, RANK><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, a, b, P, ctx->arith_flag);
+    FEO_LAUNCH_CHECK(ctx);
+    return FEO_OK;
+}
+template <typename T, int OP>
+int launch_flat_bcast(feo_ctx *ctx, T *out, const T *a, const T *b, const Collapsed &c) {
+    if (c.rank > 4 || !feo_aligned16(out)) return -1;
+    const long long lim = (1ll << 31) - 8;
+    long long n = 1, ea = 0, eb = 0;
+    for (int d = 0; d < c.rank; ++d) { n *= c.ext[d]; ea += (c.ext[d] - 1) * c.sa[d]; eb += (c.ext[d] - 1) * c.sb[d]; }
+    if (n >= lim || ea >= lim || eb >= lim) return -1;
+    switch (c.rank) {
+    case 1: return launch_flat_bcast_rank<T, OP, 1>(ctx, out, a, b, c);
+    case 2: return launch_flat_bcast_rank<T, OP, 2>(ctx, out, a, b, c);
+    case 3: return launch_flat_bcast_rank<T, OP, 3>(ctx, out, a, b, c);
+    default: return launch_flat_bcast_rank<T, OP, 4>(ctx, out, a, b, c);
+    }
+}
+
 // Vector path with VB-byte accesses; returns -1 when the shape / alignment does not allow it.
 template <typename T, int OP, int VB>
 int broadcast_vec(feo_ctx *ctx, T *out, const T *a, const T *b, const Collapsed &c, int knob) {
@@ -461,10 +589,24 @@ int broadcast_vec(feo_ctx *ctx, T *out, const T *a, const T *b, const Collapsed 
         S.nl = P.np; S.ss_l = P.sa_p; S.so_l = P.so_p;
         return launch_stream<T, OP, true, VB, 1, 4, 2, true>(ctx, out, b, a, S);
     }
-    // no invariance to exploit (or tiling disabled): 1x1 vector tiles; fold P/Q back into the rest dims
+    // no invariance to exploit (or tiling disabled): fold P/Q back into the rest dims
     if (pd >= 0) { P.rest_ext[P.nrest] = P.np; P.rest_sa[P.nrest] = P.sa_p; P.rest_sb[P.nrest] = P.sb_p; P.rest_so[P.nrest] = P.so_p; P.nrest++; }
     if (qd >= 0) { P.rest_ext[P.nrest] = P.nq; P.rest_sa[P.nrest] = P.sa_q; P.rest_sb[P.nrest] = P.sb_q; P.rest_so[P.nrest] = P.so_q; P.nrest++; }
     P.np = P.nq = 1; P.sa_p = P.sb_p = P.so_p = P.sa_q = P.sb_q = P.so_q = 0;
+    if (knob != 3 && P.nrest > 0) {
+        // e.g. matrix (op) column vector (b's inner stride is 0: a splat): nothing is re-used, but a thread that moves one
+        // vector has one load in flight.  Walk the largest outer dim as the q loop instead: 4 rows per thread in flight, and
+        // the block's spare thread rows (short inner extents) spread over it too.
+        int big = 0;
+        for (int d = 1; d < P.nrest; ++d)
+            if (P.rest_ext[d] > P.rest_ext[big]) big = d;
+        P.nq = P.rest_ext[big]; P.sa_q = P.rest_sa[big]; P.sb_q = P.rest_sb[big]; P.so_q = P.rest_so[big];
+        for (int d = big; d + 1 < P.nrest; ++d) {
+            P.rest_ext[d] = P.rest_ext[d + 1]; P.rest_sa[d] = P.rest_sa[d + 1]; P.rest_sb[d] = P.rest_sb[d + 1]; P.rest_so[d] = P.rest_so[d + 1];
+        }
+        P.nrest--;
+        return launch_tile<T, OP, VB, 1, 4, false, true>(ctx, out, a, b, P);
+    }
     P.ty = 1;  // q extent is 1: spare rows of threads would idle, keep the block one row wide
     P.tx = kThreads;
     P.i_blocks = (P.ni_vec + P.tx - 1) / P.tx;
@@ -490,6 +632,8 @@ int broadcast_typed(feo_ctx *ctx, T *out, const T *a, const T *b, int rank, cons
     if (knob != 4) {
         int rc = -1;
         rc = broadcast_vec<T, OP, 16>(ctx, out, a, b, c, knob);
+        if (rc != -1) return rc;
+        rc = launch_flat_bcast<T, OP>(ctx, out, a, b, c);
         if (rc != -1) return rc;
     }
     return launch_generic<T, OP>(ctx, out, a, b, c);

@@ -151,6 +151,18 @@ template <typename T> struct Acc<T, K_WELFORD> {
         n = nn;
     }
     __device__ __forceinline__ void merge(const Acc &o) { merge_raw(o.n, o.mean, o.m2); }
+    // the first cnt of N values (the others are 0), two-pass in registers like push_batch
+    template <int N> __device__ __forceinline__ void push_masked(const T (&x)[N], int cnt) {
+        T s = (T)0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) s += x[i];
+        const T bm = s / (T)cnt;
+        T q = (T)0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { const T c = x[i] - bm; q += (i < cnt) ? c * c : (T)0; }
+        if (n == (T)0) { n = (T)cnt; mean = bm; m2 = q; }
+        else merge_raw((T)cnt, bm, q);
+    }
     template <int N> __device__ __forceinline__ void push_batch(const T (&x)[N]) {
         T s = (T)0;
 #pragma unroll
@@ -292,7 +304,9 @@ struct Geom {
 };
 
 // ---- cols: in[k1][r1][k2] -> out[k1][k2], threads along k2 ---------------------------------------------
-template <typename T, int KIND, int LOADER, bool VEC>
+// J column-vectors per thread (kThreads apart): J = 1 with 8 rows in flight is the streaming shape; J = 4 is used when
+// there are fewer than 8 rows in all ([2, n] or [3, n] over axis 0: the loads in flight come from the columns instead).
+template <typename T, int KIND, int LOADER, bool VEC, int J>
 __global__ void __launch_bounds__(kThreads, 3) reduce_cols_kernel(T *__restrict__ out, void *__restrict__ partial,
                                                                const T *__restrict__ in, const T *__restrict__ in2,
                                                                const T *__restrict__ aux, const __grid_constant__ Geom G,
@@ -304,48 +318,177 @@ __global__ void __launch_bounds__(kThreads, 3) reduce_cols_kernel(T *__restrict_
     const long long bx = blk % G.xblocks; blk /= G.xblocks;
     const long long s = blk % G.S;
     const long long k1 = blk / G.S;
-    const long long kv = bx * kThreads + threadIdx.x;
+    const long long kv = bx * (kThreads * J) + threadIdx.x;
     if (kv * W >= G.K2) return;
     const long long r_lo = s * G.c1;
     const long long r_hi = (r_lo + G.c1 < G.R1) ? r_lo + G.c1 : G.R1;
     const long long o0 = k1 * G.K2 + kv * W;
     const T *base = in + (k1 * G.R1) * G.K2 + kv * W;
-    Acc<T, KIND> acc[W];
+    Acc<T, KIND> acc[J][W];
+    bool live[J];
 #pragma unroll
-    for (int k = 0; k < W; ++k) acc[k].init(aux_val<KIND>(aux, o0 + k));
+    for (int j = 0; j < J; ++j) {
+        live[j] = (kv + (long long)j * kThreads) * W < G.K2;
+#pragma unroll
+        for (int k = 0; k < W; ++k) acc[j][k].init(live[j] ? aux_val<KIND>(aux, o0 + (long long)j * kThreads * W + k) : (T)0);
+    }
     long long r = r_lo;
     for (; r + U <= r_hi; r += U) {
-        V v[U];
+        V v[J][U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = ld_stream(reinterpret_cast<const V *>(base + (r + u) * G.K2));
+        for (int j = 0; j < J; ++j)
+            if (live[j]) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) v[j][u] = ld_stream(reinterpret_cast<const V *>(base + (r + u) * G.K2) + (long long)j * kThreads);
+            }
         if constexpr (LOADER == LD_VECMAT) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const T w = __ldg(in2 + r + u);
 #pragma unroll
-                for (int k = 0; k < W; ++k) v[u].v[k] = w_mul(w, v[u].v[k]);
+                for (int j = 0; j < J; ++j)
+#pragma unroll
+                    for (int k = 0; k < W; ++k) v[j][u].v[k] = w_mul(w, v[j][u].v[k]);
             }
         }
 #pragma unroll
-        for (int k = 0; k < W; ++k) {
-            T x[U];
+        for (int j = 0; j < J; ++j)
+            if (live[j]) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) x[u] = v[u].v[k];
-            acc[k].push_batch(x);
+                for (int k = 0; k < W; ++k) {
+                    T x[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) x[u] = v[j][u].v[k];
+                    acc[j][k].push_batch(x);
+                }
+            }
+    }
+    // fewer than U rows left (or, with few rows in all, the whole job): TU rows x J columns of loads go out together
+    constexpr int TU = (J == 1) ? 4 : 2;
+    for (; r < r_hi; r += TU) {
+        const int nrem = (int)((r_hi - r < TU) ? r_hi - r : TU);
+        V v[J][TU];
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+            if (live[j]) {
+#pragma unroll
+                for (int u = 0; u < TU; ++u)
+                    if (u < nrem) v[j][u] = ld_stream(reinterpret_cast<const V *>(base + (r + u) * G.K2) + (long long)j * kThreads);
+            }
+#pragma unroll
+        for (int u = 0; u < TU; ++u)
+            if (u < nrem) {
+                T w = (T)1;
+                if constexpr (LOADER == LD_VECMAT) w = __ldg(in2 + r + u);
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+                    if (live[j]) {
+#pragma unroll
+                        for (int k = 0; k < W; ++k) acc[j][k].push(LOADER == LD_VECMAT ? w_mul(w, v[j][u].v[k]) : v[j][u].v[k]);
+                    }
+            }
+    }
+    if (VEC && G.S <= 1 && G.fin != FIN_MEAN_M2) {
+        // unsplit: one 128-bit store per column-vector (with few rows the output is as large as the input, and W scalar
+        // stores per thread, 16 bytes apart across the warp, quarter-fill every sector they touch)
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+            if (live[j]) {
+                V r;
+#pragma unroll
+                for (int k = 0; k < W; ++k) {
+                    if constexpr (KIND == K_WELFORD) r.v[k] = acc[j][k].m2 / divisor;
+                    else r.v[k] = (G.fin == FIN_DIV) ? w_div(acc[j][k].v, divisor, flag) : acc[j][k].v;
+                }
+                *reinterpret_cast<V *>(out + o0 + (long long)j * kThreads * W) = r;
+            }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+        if (live[j]) {
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+                emit(acc[j][k], out, partial, o0 + (long long)j * kThreads * W + k, s, G.nout, G.S, G.fin, divisor, flag, G.counters);
+        }
+}
+
+// ---- cols2d: in[k1][r1][k2] with a SHORT k2 row (at most 128 vectors: [n, 3] points, [.., 4096, 16] ...) ---------------
+// The cols kernel would leave most of a block idle (k2 = 16: 4 of 256 threads).  Here a block owns one (k1, split): its
+// threads form an lx x ly grid, lx = k2 / W lanes across the row (any value, not only powers of two), ly = 256 / lx rows
+// walked concurrently with 8 sweeps in flight; so a warp still reads whole contiguous rows.  The ly partial rows are
+// combined through shared memory in a fixed tree.
+template <typename T, int KIND, int LOADER, bool VEC>
+__global__ void __launch_bounds__(kThreads) reduce_cols2d_kernel(T *__restrict__ out, void *__restrict__ partial,
+                                                                 const T *__restrict__ in, const T *__restrict__ in2,
+                                                                 const T *__restrict__ aux, const __grid_constant__ Geom G,
+                                                                 T divisor, int *flag) {
+    constexpr int W = VEC ? VecN<T>::value : 1;
+    constexpr int U = 8;
+    using V = AVec<T, W>;
+    __shared__ Acc<T, KIND> smem[W][kThreads];
+    // lx x ly threads per k1; when the rows are few and short, several k1 share a block (G.c2 of them)
+    const int lx = G.lx, ly = G.lanes, per = lx * ly, kz = (int)G.c2;
+    const int tz = threadIdx.x / per, tin = threadIdx.x % per;
+    const int tx = tin % lx, ty = tin / lx;
+    const long long s = blockIdx.x % G.S, k1 = (blockIdx.x / G.S) * kz + tz;
+    const bool active = tz < kz && k1 < G.K1;
+    const long long r_lo = s * G.c1;
+    const long long r_hi = (r_lo + G.c1 < G.R1) ? r_lo + G.c1 : G.R1;
+    const long long o0 = k1 * G.K2 + (long long)tx * W;
+    Acc<T, KIND> acc[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) acc[k].init(active ? aux_val<KIND>(aux, o0 + k) : (T)0);
+    if (active) {
+        const T *base = in + (k1 * G.R1) * G.K2 + (long long)tx * W;
+        long long r = r_lo + ty;
+        for (; r + (long long)(U - 1) * ly < r_hi; r += (long long)U * ly) {
+            V v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = ld_stream(reinterpret_cast<const V *>(base + (r + (long long)u * ly) * G.K2));
+            if constexpr (LOADER == LD_VECMAT) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const T w = __ldg(in2 + r + (long long)u * ly);
+#pragma unroll
+                    for (int k = 0; k < W; ++k) v[u].v[k] = w_mul(w, v[u].v[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < W; ++k) {
+                T x[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) x[u] = v[u].v[k];
+                acc[k].push_batch(x);
+            }
+        }
+        for (; r < r_hi; r += ly) {
+            V v = ld_stream(reinterpret_cast<const V *>(base + r * G.K2));
+            if constexpr (LOADER == LD_VECMAT) {
+                const T w = __ldg(in2 + r);
+#pragma unroll
+                for (int k = 0; k < W; ++k) v.v[k] = w_mul(w, v.v[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < W; ++k) acc[k].push(v.v[k]);
         }
     }
-    for (; r < r_hi; ++r) {
-        V v = ld_stream(reinterpret_cast<const V *>(base + r * G.K2));
-        if constexpr (LOADER == LD_VECMAT) {
-            const T w = __ldg(in2 + r);
 #pragma unroll
-            for (int k = 0; k < W; ++k) v.v[k] = w_mul(w, v.v[k]);
+    for (int k = 0; k < W; ++k) smem[k][threadIdx.x] = acc[k];
+    __syncthreads();
+    int st = 1;
+    while (st * 2 < ly) st *= 2;  // largest power of two below ly (ly >= 2)
+    for (; st >= 1; st >>= 1) {
+        if (active && ty < st && ty + st < ly) {
+#pragma unroll
+            for (int k = 0; k < W; ++k) smem[k][threadIdx.x].merge(smem[k][threadIdx.x + st * lx]);
         }
-#pragma unroll
-        for (int k = 0; k < W; ++k) acc[k].push(v.v[k]);
+        __syncthreads();
     }
+    if (active && ty == 0) {
 #pragma unroll
-    for (int k = 0; k < W; ++k) emit(acc[k], out, partial, o0 + k, s, G.nout, G.S, G.fin, divisor, flag, G.counters);
+        for (int k = 0; k < W; ++k) emit(smem[k][threadIdx.x], out, partial, o0 + k, s, G.nout, G.S, G.fin, divisor, flag, G.counters);
+    }
 }
 
 // ---- micro: in[k1][r1][k2][r2] with 2 <= r2 <= 32 ----------------------------------------------------------
@@ -354,7 +497,7 @@ __global__ void __launch_bounds__(kThreads, 3) reduce_cols_kernel(T *__restrict_
 // R2C == 0: run-time r2, one output per thread, scalar loads.
 // WIDE (r1 == 1: a single row per output): no row loop to unroll, so more outputs per thread keep ~256 B in flight.
 template <int R2C, bool WIDE> struct MicroShape {
-    static constexpr int OUTS = (R2C == 0) ? 1 : (WIDE ? ((32 / R2C) > 8 ? 8 : ((32 / R2C) < 2 ? 2 : (32 / R2C))) : (R2C <= 16 ? 4 : 2));
+    static constexpr int OUTS = (R2C == 0) ? 4 : (WIDE ? ((32 / R2C) > 8 ? 8 : ((32 / R2C) < 2 ? 2 : (32 / R2C))) : (R2C <= 16 ? 4 : 2));
     static constexpr int U = (R2C == 0 || WIDE) ? 1 : ((64 / (OUTS * R2C)) > 8 ? 8 : ((64 / (OUTS * R2C)) < 1 ? 1 : (64 / (OUTS * R2C))));
 };
 template <typename T, int KIND, int R2C, bool WIDE>
@@ -455,9 +598,29 @@ __global__ void __launch_bounds__(kThreads) reduce_micro_kernel(T *__restrict__ 
         }
         }
     } else {
+        // run-time r2 (3, 5, 6 ... or an unaligned base): a thread still owns whole outputs; its 4-byte loads go through
+        // L1, which turns the warp's stride-r2 accesses back into full sectors.  Groups of 8 loads are issued together.
+        const int r2 = (int)G.R2;
         for (long long r = r_lo; r < r_hi; ++r) {
             const T *p = base + r * rstride;
-            for (long long j = 0; j < G.R2; ++j) acc[0].push(__ldg(p + j));
+            for (int j0 = 0; j0 < r2; j0 += 8) {
+                T x[OUTS][8];
+#pragma unroll
+                for (int o = 0; o < OUTS; ++o)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[o][j] = (live[o] && j0 + j < r2) ? __ldg(p + (long long)o * kThreads * G.R2 + j0 + j) : (T)0;
+                const int cnt = (r2 - j0 < 8) ? r2 - j0 : 8;
+#pragma unroll
+                for (int o = 0; o < OUTS; ++o) {
+                    if constexpr (KIND == K_WELFORD) {
+                        acc[o].push_masked(x[o], cnt);  // masked lanes hold 0: one division per chunk instead of one per element
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < cnt) acc[o].push(x[o][j]);
+                    }
+                }
+            }
         }
     }
     if constexpr (!(R2C > 0 && WIDE)) {  // the WIDE path has emitted and returned above
@@ -474,7 +637,7 @@ __global__ void __launch_bounds__(kThreads, 4) reduce_rows_kernel(T *__restrict_
                                                                const T *__restrict__ aux, const __grid_constant__ Geom G,
                                                                T divisor, int *flag) {
     constexpr int W = VEC ? VecN<T>::value : 1;
-    constexpr int U = 4;
+    constexpr int U = VEC ? 4 : 16;  // scalar path (odd / unaligned rows): 16 four-byte loads in flight per lane
     using V = AVec<T, W>;
     __shared__ Acc<T, KIND> smem[kThreads / 32];
     const int lanes = G.lanes;
@@ -503,6 +666,40 @@ __global__ void __launch_bounds__(kThreads, 4) reduce_rows_kernel(T *__restrict_
             const T *row2 = nullptr;
             if constexpr (LOADER == LD_MUL) row2 = in2 + obase + r * rstride;
             if constexpr (LOADER == LD_MATVEC) row2 = in2;
+            if constexpr (!VEC && LOADER == LD_PLAIN) {
+                // odd or unaligned rows (e.g. 4099 columns): peel each row segment to a 16-byte boundary and read its body
+                // with 128-bit loads like the aligned path; the <= 2 * (VN - 1) edge elements go through scalar loads
+                constexpr int VNp = VecN<T>::value;
+                constexpr int UP = 4;
+                using VP = AVec<T, VNp>;
+                const T *seg = row + c_lo;
+                const long long len = c_hi - c_lo;
+                const int mis = (int)((reinterpret_cast<uintptr_t>(seg) / sizeof(T)) % VNp);
+                long long head = mis ? VNp - mis : 0;
+                if (head > len) head = len;
+                for (long long e = lxi; e < head; e += lx) acc.push(__ldg(seg + e));
+                const VP *body = reinterpret_cast<const VP *>(seg + head);
+                const long long nb = (len - head) / VNp;
+                long long bv = lxi;
+                for (; bv + (long long)(UP - 1) * lx < nb; bv += (long long)UP * lx) {
+                    VP v[UP];
+#pragma unroll
+                    for (int u = 0; u < UP; ++u) v[u] = ld_stream(body + bv + (long long)u * lx);
+                    T x[UP * VNp];
+#pragma unroll
+                    for (int u = 0; u < UP; ++u)
+#pragma unroll
+                        for (int k = 0; k < VNp; ++k) x[u * VNp + k] = v[u].v[k];
+                    acc.push_batch(x);
+                }
+                for (; bv < nb; bv += lx) {
+                    const VP v = ld_stream(body + bv);
+#pragma unroll
+                    for (int k = 0; k < VNp; ++k) acc.push(v.v[k]);
+                }
+                for (long long e = head + nb * VNp + lxi; e < len; e += lx) acc.push(__ldg(seg + e));
+                continue;
+            }
             long long cv = c_lo + lxi;
             for (; cv + (long long)(U - 1) * lx < c_hi; cv += (long long)U * lx) {
                 V v[U];
@@ -716,15 +913,35 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
     const long long target_blocks = (long long)ctx->sm_count * (ctx->knobs[FEO_KNOB_REDUCE_BLOCKS_PER_SM] > 0 ? ctx->knobs[FEO_KNOB_REDUCE_BLOCKS_PER_SM] : 8);
     const int forced = ctx->knobs[FEO_KNOB_REDUCE_SPLIT];
     const bool in_aligned = feo_aligned16(in) && (LOADER == LD_PLAIN || LOADER == LD_VECMAT || feo_aligned16(in2));
-    enum { COLS, MICRO, ROWS } which;
+    enum { COLS, COLS2D, MICRO, ROWS } which;
     bool vec = false;
-    int r2c = 0;
+    int r2c = 0, cols_j = 1;
 
-    if (c.R2 == 1 && LOADER != LD_MUL && LOADER != LD_MATVEC) {
-        which = COLS;
+    if (c.R2 == 1 && LOADER != LD_MUL && LOADER != LD_MATVEC && c.R1 >= 2 &&
+        c.K2 / ((in_aligned && c.K2 % VN == 0) ? VN : 1) <= kThreads / 2) {
+        which = COLS2D;  // short rows: lx lanes across k2, ly rows at a time
         vec = in_aligned && (c.K2 % VN == 0);
         const long long W = vec ? VN : 1;
-        G.xblocks = feo_ceil_div((size_t)(c.K2 / W), (size_t)kThreads);
+        G.lx = (int)(c.K2 / W);
+        G.lanes = kThreads / G.lx;  // ly
+        if ((long long)G.lanes > c.R1) G.lanes = (int)c.R1;
+        long long kz = kThreads / ((long long)G.lx * G.lanes);  // k1 per block
+        if (kz > c.K1) kz = c.K1;
+        G.c2 = kz;
+        G.xblocks = feo_ceil_div((size_t)c.K1, (size_t)kz);  // blocks along k1
+        const long long want = 4 * target_blocks;
+        long long S = forced > 0 ? forced : feo_ceil_div((size_t)want, (size_t)G.xblocks);
+        const long long min_rows = (long long)G.lanes * 16;  // two full sweeps per thread
+        S = clampll(S, 1, c.R1 / min_rows > 0 ? c.R1 / min_rows : 1);
+        G.c1 = feo_ceil_div((size_t)c.R1, (size_t)S);
+        G.S = G.S1 = feo_ceil_div((size_t)c.R1, (size_t)G.c1);
+    } else if (c.R2 == 1 && LOADER != LD_MUL && LOADER != LD_MATVEC) {
+        which = COLS;
+        vec = in_aligned && (c.K2 % VN == 0) && feo_aligned16(out);
+        const long long W = vec ? VN : 1;
+        // few rows: the columns must supply the loads in flight, 4 column-vectors per thread
+        cols_j = (c.R1 < 8 && c.K2 / W >= 4 * kThreads) ? 4 : 1;
+        G.xblocks = feo_ceil_div((size_t)(c.K2 / W), (size_t)kThreads * cols_j);
         const long long base_blocks = G.xblocks * c.K1;
         long long S = forced > 0 ? forced : feo_ceil_div((size_t)target_blocks, (size_t)base_blocks);
         S = clampll(S, 1, c.R1 >= 32 ? c.R1 / 16 : 1);
@@ -736,7 +953,7 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         for (int i = 0; i < 5; ++i)
             if (c.R2 == cands[i] && feo_aligned32(in)) r2c = cands[i];
         const bool wide = (c.R1 == 1);
-        int outs = r2c == 0 ? 1 : (r2c <= 16 ? 4 : 2);  // MicroShape<R2C, WIDE>::OUTS
+        int outs = r2c == 0 ? 4 : (r2c <= 16 ? 4 : 2);  // MicroShape<R2C, WIDE>::OUTS
         if (r2c && wide) { outs = 32 / r2c; outs = outs > 8 ? 8 : (outs < 2 ? 2 : outs); }
         G.xblocks = feo_ceil_div((size_t)c.K2, (size_t)kThreads * outs);
         const long long base_blocks = G.xblocks * c.K1;
@@ -750,7 +967,9 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         const long long W = vec ? VN : 1;
         const long long nvec = c.R2 / W;
         const long long per_out = c.R1 * c.R2;
-        G.lanes = (per_out >= 4096) ? kThreads : 32;
+        // a block per output for long rows -- unless the outputs alone fill the machine with warps (65536 rows of 4099)
+        const bool many_outputs = G.nout >= 16 * target_blocks && per_out < 65536;
+        G.lanes = (per_out >= 4096 && !many_outputs) ? kThreads : 32;
         const long long outs_per_block = kThreads / G.lanes;
         const long long base_blocks = feo_ceil_div((size_t)G.nout, (size_t)outs_per_block);
         const long long want = 4 * target_blocks;  // several waves of small units: no ragged last wave
@@ -763,9 +982,10 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         S1 = feo_ceil_div((size_t)c.R1, (size_t)G.c1);
         long long S2 = feo_ceil_div((size_t)S, (size_t)S1);
         long long c2 = feo_ceil_div((size_t)nvec, (size_t)S2);
+        const long long sweep = vec ? 4 : 16;  // U of the rows kernel: loads per lane per sweep
         int lx = 1;
-        while (lx < G.lanes && (long long)lx * 4 < c2) lx *= 2;  // U = 4 vectors per lane per sweep
-        const long long quantum = (long long)lx * 4;
+        while (lx < G.lanes && (long long)lx * sweep < c2) lx *= 2;
+        const long long quantum = (long long)lx * sweep;
         c2 = feo_ceil_div((size_t)c2, (size_t)quantum) * quantum;
         S2 = feo_ceil_div((size_t)nvec, (size_t)c2);
         G.lx = lx;
@@ -792,8 +1012,16 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         const long long blocks = G.xblocks * G.S * c.K1;
         if (blocks > 0x7fffffffLL) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "reduction grid too large");
         constexpr int L = (LOADER == LD_VECMAT) ? LD_VECMAT : LD_PLAIN;
-        if (vec) reduce_cols_kernel<T, KIND, L, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
-        else reduce_cols_kernel<T, KIND, L, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
+        if (vec && cols_j == 1) reduce_cols_kernel<T, KIND, L, true, 1><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
+        else if (vec) reduce_cols_kernel<T, KIND, L, true, 4><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
+        else if (cols_j == 1) reduce_cols_kernel<T, KIND, L, false, 1><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
+        else reduce_cols_kernel<T, KIND, L, false, 4><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
+    } else if (which == COLS2D) {
+        const long long blocks = G.S * G.xblocks;
+        if (blocks > 0x7fffffffLL) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "reduction grid too large");
+        constexpr int L = (LOADER == LD_VECMAT) ? LD_VECMAT : LD_PLAIN;
+        if (vec) reduce_cols2d_kernel<T, KIND, L, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
+        else reduce_cols2d_kernel<T, KIND, L, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
     } else if (which == MICRO) {
         const long long blocks = G.xblocks * G.S * c.K1;
         if (blocks > 0x7fffffffLL) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "reduction grid too large");

@@ -257,6 +257,14 @@ BCAST_CASES = [
     ((2, 3, 1, 16), (2, 1, 5, 16)),
     ((1,), (1,)),
     ((6, 1, 32), (6, 4, 1)),            # b splat along the inner axis, a invariant along dim 1
+    ((300, 64), (300, 1)),              # matrix (op) column vector: no invariant dim, 4 rows in flight per thread
+    ((70, 33, 256), (70, 33, 1)),       # the same with a short inner extent (spare thread rows walk the outer dim)
+    ((500, 3), (1, 3)),                 # inner extent 3: flat-index kernel, vectors straddle rows
+    ((500, 3), (500, 1)), ((1, 3), (500, 3)),
+    ((41, 1, 7), (1, 13, 7)),           # flat-index kernel, rank 3
+    ((9, 1, 5, 3), (1, 4, 5, 1)),       # rank 4, inner splat
+    ((257, 1), (1, 4099)),              # outer product with an odd row length
+    ((3, 1, 5, 1, 7, 3), (1, 2, 1, 4, 7, 3)),  # rank 5 after collapsing: generic fallback
 ]
 
 
@@ -312,6 +320,11 @@ REDUCE_CASES = [
     ((4097, 33), [0]), ((20000, 4), [0]), ((7, 9), [0]), ((1, 9), [0]), ((9, 1), [0]),             # cols: ragged / tiny
     ((3, 4, 5, 6, 7), [0, 2, 4]), ((3, 4, 5, 6, 7), [1, 3]), ((2, 3, 4, 5, 6, 7), [0, 2, 4]),      # >4 groups: generic
     ((6, 5, 4, 3), [1, 3]), ((6, 5, 4, 3), [0, 2]), ((6, 5, 4, 3), [1, 2]),
+    ((5000, 3), [0]), ((5000, 16), [0]), ((40, 300, 16), [1]), ((40, 300, 3), [1]), ((7, 2, 12), [1]),   # cols2d: short k2 rows
+    ((9, 5000, 7), [1]), ((3, 100, 500), [1]), ((100, 128 * 4), [0]),                                 # cols2d at its lx limits / cols
+    ((2, 5000), [0]), ((3, 4099), [0]), ((5, 8192), [0]), ((3, 3000, 1025), [1]),                     # cols with few rows, scalar columns
+    ((300, 4099), [1]), ((64, 1 << 15), [1]), ((17, 100001), [1]),                                    # rows, unaligned lengths
+    ((200, 5, 11), [0, 2]), ((4000, 9), [1]), ((300, 31), [1]), ((300, 17, 3), [2]),                  # micro, run-time r2 incl. > 8
     ((1,), [0]), ((1, 1, 1), [1]), ((2, 1, 3), [1]),
 ]
 
@@ -379,6 +392,30 @@ def test_reduction_split_counts_agree(feo, oracle):
     finally:
         ctx.tune(L.KNOB_REDUCE_SPLIT, 0)
         ctx.tune(L.KNOB_REDUCE_FUSE, 0)
+
+
+def test_many_group_reductions_multipass_and_generic_agree(feo, oracle):
+    """More than four alternating kept / reduced groups: the multi-pass route (sum / mean / max / min) and the
+    one-kernel generic fallback (knob REDUCE_SPLIT = -1; always used for var) give the oracle's integers bit for bit."""
+    import feotensor_b200._lib as L
+    ctx = feo.Context.default()
+    rng = np.random.default_rng(302)
+    cases = [((3, 4, 5, 6, 7), [0, 2, 4]), ((3, 4, 5, 6, 7), [1, 3]), ((2, 3, 4, 5, 6, 7), [0, 2, 4]), ((2, 3, 4, 5, 6, 7), [1, 3, 5]),
+             ((4, 3, 5, 2, 6, 3, 7), [0, 2, 4, 6]), ((4, 3, 5, 2, 6, 3, 7), [1, 3, 5]), ((8, 9, 10, 11, 12), [0, 2, 4])]
+    try:
+        for shape, axes in cases:
+            x = rand(oracle, rng, "i32", shape)
+            xf = rand(oracle, rng, "f64", shape)
+            t, tf = feo.Tensor(feo.Shape(shape), x), feo.Tensor(feo.Shape(shape), xf)
+            for knob in (0, -1):
+                ctx.tune(L.KNOB_REDUCE_SPLIT, knob)
+                for kind in ("sum", "mean", "var", "max", "min"):
+                    np.testing.assert_array_equal(getattr(t, kind)(axes).to_numpy(), oracle.reduce(kind, x, axes), err_msg=f"{knob} {kind} {shape} {axes}")
+                np.testing.assert_array_equal(tf.max(axes).to_numpy(), oracle.reduce("max", xf, axes))
+                np.testing.assert_allclose(tf.sum(axes).to_numpy(), oracle.reduce("sum", xf, axes), rtol=1e-12, atol=1e-12)
+                np.testing.assert_allclose(tf.mean(axes).to_numpy(), oracle.reduce("mean", xf, axes), rtol=1e-12, atol=1e-13)
+    finally:
+        ctx.tune(L.KNOB_REDUCE_SPLIT, 0)
 
 
 def test_mean_divisor_quirk_on_device(feo, oracle):
