@@ -293,12 +293,16 @@ def test_broadcast_tile_variants_agree(feo, oracle):
     ta, tb = feo.Tensor(feo.shape(19, 1, 256), a), feo.Tensor(feo.shape(1, 23, 256), b)
     want = oracle.ewise_broadcast("mul", a, b)
     try:
-        for knob in (0, 2, 3, 4):
+        for knob in (0, 2, 3, 4, 5, 6):
             for lchunk in (0, 1, 5, 64):
                 ctx.tune(L.KNOB_BCAST_TILE, knob)
                 ctx.tune(L.KNOB_BCAST_LCHUNK, lchunk)
                 np.testing.assert_array_equal(ta.broadcast("mul", tb).to_numpy(), want, err_msg=f"knob {knob} lchunk {lchunk}")
                 np.testing.assert_array_equal(ta.broadcast("sub", tb).to_numpy(), oracle.ewise_broadcast("sub", a, b))
+                # matrix (op) row vector: plain 4-rows-in-flight path (auto, 5) vs hold + stream (6)
+                m, r = rand(oracle, rng, "f32", (37, 192)), rand(oracle, rng, "f32", (1, 192))
+                np.testing.assert_array_equal(feo.Tensor(feo.shape(37, 192), m).broadcast("div", feo.Tensor(feo.shape(1, 192), r)).to_numpy(),
+                                              oracle.ewise_broadcast("div", m, r), err_msg=f"knob {knob}")
     finally:
         ctx.tune(L.KNOB_BCAST_TILE, 0)
         ctx.tune(L.KNOB_BCAST_LCHUNK, 0)

@@ -21,6 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--only", default="")
+    ap.add_argument("--tile", type=int, default=0, help="FEO_KNOB_BCAST_TILE")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -33,6 +34,7 @@ def main():
     ctx = feo.Context(0)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     lib, h, vp = ctx.lib, ctx.handle, C.c_void_p
+    ctx.tune(L.KNOB_BCAST_TILE, args.tile)
 
     def dev(nbytes):
         return torch.empty(nbytes, dtype=torch.uint8, device="cuda")
@@ -95,6 +97,8 @@ def main():
         ("f32", [64, 64, 64, 1024], [1, 0, 1, 0], [0, 1, 0, 1]), ("f32", [65536, 4099], [1, 0], [0, 1]), ("f32", [4099, 65536], [1, 0], [0, 1]),
         ("f64", [4096, 4096, 8], [1, 0, 1], [0, 1, 1]), ("i32", [4096, 4096, 16], [1, 0, 1], [0, 1, 1]), ("i64", [8192, 8192], [1, 0], [0, 1]),
         ("f32", [16, 16, 16, 16, 16, 16, 16], [1, 0, 1, 0, 1, 0, 1], [0, 1, 0, 1, 0, 1, 0]),
+        ("f32", [1048576, 256], [1, 1], [0, 1]), ("f32", [65536, 4096], [1, 1], [0, 1]), ("f32", [4096, 65536], [1, 1], [0, 1]),
+        ("f32", [4096, 65536], [0, 1], [1, 1]), ("f64", [16384, 8192], [1, 1], [0, 1]),
     ]
     if args.only in ("", "bcast"):
         for dt, shape, am, bm in bcast_cases:
