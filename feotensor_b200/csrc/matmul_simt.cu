@@ -21,7 +21,7 @@ template <typename T> __device__ __forceinline__ T mac(T acc, T a, T b) {
 }
 
 template <typename T, bool FAST>
-__global__ void __launch_bounds__(kThreads) matmul_simt_kernel(T *__restrict__ C, const T *__restrict__ A,
+__global__ void __launch_bounds__(kThreads, (sizeof(T) == 4 ? 2 : 1)) matmul_simt_kernel(T *__restrict__ C, const T *__restrict__ A,
                                                                const T *__restrict__ B, long long M, long long K, long long N) {
     constexpr int VN = VecN<T>::value;        // elements per 128-bit access
     constexpr int BK = 4 * VN;                // 16 (4-byte) or 8 (8-byte): four vectors per A-tile row

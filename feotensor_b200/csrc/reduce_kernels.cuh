@@ -875,6 +875,32 @@ __global__ void __launch_bounds__(kThreads) reduce_generic_kernel(T *__restrict_
     }
 }
 
+// Second stage of a many-group float variance: the input is an array of equal-count Welford partials (means in `mean`,
+// M2 in `m2`, `count` elements each) laid out densely over the remaining groups; a warp merges the partials of one output
+// in a fixed order (Chan).  The data is the small intermediate of the first, canonical pass, so simplicity wins here.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) reduce_generic_pairs_kernel(T *__restrict__ out, const T *__restrict__ mean,
+                                                                        const T *__restrict__ m2, const __grid_constant__ GenericGeom G,
+                                                                        T count, T divisor, int *flag) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (kThreads / 32);
+    for (long long o = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); o < G.nout; o += warps) {
+        long long rem = o, base = 0;
+#pragma unroll 1
+        for (int d = G.nk - 1; d >= 0; --d) { base += (rem % G.kext[d]) * G.kstr[d]; rem /= G.kext[d]; }
+        Acc<T, K_WELFORD> acc;
+        acc.init((T)0);
+        for (long long i = lane; i < G.nred; i += 32) {
+            long long q = i, off = base;
+#pragma unroll 1
+            for (int d = G.nr - 1; d >= 0; --d) { off += (q % G.rext[d]) * G.rstr[d]; q /= G.rext[d]; }
+            acc.merge_raw(count, __ldg(mean + off), __ldg(m2 + off));
+        }
+        warp_merge(acc);
+        if (lane == 0) finalize(acc, out, o, G.nout, G.fin, divisor, flag);
+    }
+}
+
 // ---- stage 2: merge S partial accumulators per output, in a fixed order (deterministic) -------------------------
 // MODE 0: a thread per output (many outputs); 1: a warp per output; 2: a CTA per output (few outputs, thousands of splits:
 // a full reduction of 1 GiB leaves ~4700 partials, which one warp merged in ~100 us).  Warp / CTA: every lane takes a

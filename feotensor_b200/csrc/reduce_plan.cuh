@@ -3,6 +3,8 @@
 #pragma once
 #include <string.h>
 
+#include <utility>
+
 #include "reduce_kernels.cuh"
 
 using namespace feo_red;
@@ -90,12 +92,62 @@ int run_multipass(feo_ctx *ctx, const Plan &p, T *out, const T *in, int fin, T d
     return rc;
 }
 
+// Float variance over more groups than the canonical kernels take: the innermost canonical suffix is reduced to Welford
+// partials (mean | M2, equal counts) by the fast kernels -- one pass over the input -- and the partials, 1 / (r1 * r2) of
+// the size, are merged over the remaining reduced groups by reduce_generic_pairs_kernel.
+template <typename T>
+int run_var_twostage(feo_ctx *ctx, const Plan &p, T *out, const T *in, int fin, T divisor) {
+    const int m = p.m;
+    const int take = p.red[m - 1] ? 4 : 3;
+    Canon s{true, 1, 1, 1, 1};
+    for (int i = 0; i <= m - take; ++i) s.K1 *= p.ext[i];
+    s.R1 = p.ext[m - take + 1];
+    s.K2 = p.ext[m - take + 2];
+    if (take == 4) s.R2 = p.ext[m - 1];
+    const long long n1 = s.K1 * s.K2;
+    if (s.R1 * s.R2 < 32) return -1;  // the first pass would shrink the data too little to pay for a second one
+    T *tmp = nullptr;
+    FEO_CUDA(ctx, feo_alloc_async(ctx, (void **)&tmp, (size_t)n1 * 2 * sizeof(T)));
+    int rc = run_canonical<T, K_WELFORD, LD_PLAIN>(ctx, s, tmp, in, nullptr, nullptr, FIN_MEAN_M2, (T)1);
+    if (rc == FEO_OK) {
+        // the intermediate is dense over groups 0 .. m - take (the last of them kept, extended by k2)
+        GenericGeom G;
+        memset(&G, 0, sizeof G);
+        G.nout = 1; G.nred = 1; G.fin = fin;
+        long long stride = 1;
+        for (int i = m - take; i >= 0; --i) {
+            const long long e = (i == m - take) ? p.ext[i] * s.K2 : p.ext[i];
+            if (p.red[i]) { G.rext[G.nr] = e; G.rstr[G.nr] = stride; G.nr++; G.nred *= e; }
+            else { G.kext[G.nk] = e; G.kstr[G.nk] = stride; G.nk++; G.nout *= e; }
+            stride *= e;
+        }
+        // make_plan lists dims outermost first; this loop ran innermost first
+        for (int i = 0; i < G.nk / 2; ++i) { std::swap(G.kext[i], G.kext[G.nk - 1 - i]); std::swap(G.kstr[i], G.kstr[G.nk - 1 - i]); }
+        for (int i = 0; i < G.nr / 2; ++i) { std::swap(G.rext[i], G.rext[G.nr - 1 - i]); std::swap(G.rstr[i], G.rstr[G.nr - 1 - i]); }
+        long long blocks = feo_ceil_div((size_t)G.nout, (size_t)(kThreads / 32));
+        const long long cap = (long long)ctx->sm_count * 32;
+        if (blocks > cap) blocks = cap;
+        reduce_generic_pairs_kernel<T><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, tmp, tmp + n1, G, (T)(s.R1 * s.R2), divisor, ctx->arith_flag);
+        ctx->launches++;
+        ctx->window.clear();
+        if (cudaGetLastError() != cudaSuccess) rc = feo_fail(ctx, FEO_ERR_CUDA, "reduce_generic_pairs_kernel launch failed");
+    }
+    cudaFreeAsync(tmp, ctx->stream);
+    return rc;
+}
+
 template <typename T, int KIND>
 int run_plan(feo_ctx *ctx, const Plan &p, T *out, const T *in, const T *aux, int fin, T divisor) {
     const Canon c = canonicalise(p.m, p.ext, p.red);
     if (c.ok) return run_canonical<T, KIND, LD_PLAIN>(ctx, c, out, in, nullptr, aux, fin, divisor);
     if constexpr (KIND == K_SUM || KIND == K_MAX || KIND == K_MIN) {
         if (ctx->knobs[FEO_KNOB_REDUCE_SPLIT] != -1) return run_multipass<T, KIND>(ctx, p, out, in, fin, divisor);
+    }
+    if constexpr (KIND == K_WELFORD) {
+        if (ctx->knobs[FEO_KNOB_REDUCE_SPLIT] != -1) {
+            const int rc = run_var_twostage<T>(ctx, p, out, in, fin, divisor);
+            if (rc != -1) return rc;
+        }
     }
     GenericGeom G = p.gen;
     G.fin = fin;

@@ -418,6 +418,8 @@ def test_many_group_reductions_multipass_and_generic_agree(feo, oracle):
                 np.testing.assert_array_equal(tf.max(axes).to_numpy(), oracle.reduce("max", xf, axes))
                 np.testing.assert_allclose(tf.sum(axes).to_numpy(), oracle.reduce("sum", xf, axes), rtol=1e-12, atol=1e-12)
                 np.testing.assert_allclose(tf.mean(axes).to_numpy(), oracle.reduce("mean", xf, axes), rtol=1e-12, atol=1e-13)
+                # float var: canonical Welford pass + pair merge (knob 0) or the one-kernel generic fallback (knob -1)
+                np.testing.assert_allclose(tf.var(axes).to_numpy(), oracle.reduce("var", xf, axes), rtol=1e-10, atol=1e-13)
     finally:
         ctx.tune(L.KNOB_REDUCE_SPLIT, 0)
 
