@@ -112,6 +112,28 @@ def cpu_reference_slab(oracle, np, n_slabs):
     return dt, float(out[3, 5, 7])
 
 
+def cpu_config1(oracle, np):
+    """BASELINE config 1 (the reference's own CPU-runnable case) on one host core, in ms: the structure-faithful
+    restatement (per-element coordinate vectors and flatten calls like tensor.rs:94-105), the same-order direct-index
+    port, and numpy as a courtesy second baseline."""
+    shape, axes = (64, 128, 256), [0, 2]
+    x = oracle.fill_uniform("f32", 64 * 128 * 256, SEED + 10, 0, -1.0, 1.0).reshape(shape)
+    y = oracle.fill_uniform("f32", 64 * 128 * 256, SEED + 11, 0, -1.0, 1.0).reshape(shape)
+
+    def ms(fn):
+        t0 = time.perf_counter()
+        fn()
+        return round((time.perf_counter() - t0) * 1e3, 3)
+    out = {"add": {"faithful": ms(lambda: oracle.ewise("add", x, y, faithful=True)), "port": ms(lambda: oracle.ewise("add", x, y)),
+                   "numpy": ms(lambda: x + y)}}
+    for kind, npf in (("sum", lambda: x.sum(axis=(0, 2))), ("mean", lambda: x.mean(axis=(0, 2))), ("var", lambda: x.var(axis=(0, 2)))):
+        out[kind + "_axes02"] = {"faithful": ms(lambda: oracle.reduce(kind, x, axes, faithful=True)),
+                                 "port": ms(lambda: oracle.reduce(kind, x, axes)), "numpy": ms(npf)}
+    out["note"] = ("ms on one core; 'faithful' var computes the mean once -- the reference recomputes it for each of the 128 targets "
+                   "(tensor.rs:188): multiply by ~128")
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the Rust
     crate cannot be built in this image), one host core, each step = one 1 GiB slab of the workload."""
@@ -345,6 +367,29 @@ def run_suite_sharded(torch, dist, feo, ctx, rank, world, hbm_peak, iters=10):
     return out
 
 
+def bind_to_gpu_numa_node(torch, device):
+    """Best effort: run this process on the CPUs of the NUMA node the GPU hangs off, so the pinned host buffers of the e2e
+    leg are allocated there (8 ranks writing 55 GB/s each into one socket's memory is what limits e2e at N > 1).
+    Returns the node number, or None when the topology is not visible (containers without /sys, single-node hosts)."""
+    try:
+        p = torch.cuda.get_device_properties(device)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -446,6 +491,7 @@ def main():
 
     # ---- e2e: the same metric through the C ABI with HOST buffers (H2D + kernels + D2H in the timed region) ------
     e2e_steps = max(2, min(K, 3))
+    numa_node = bind_to_gpu_numa_node(torch, local)
     a_host = torch.from_numpy(a_h.reshape(-1).copy()).pin_memory()
     b_host = torch.from_numpy(b_h.reshape(-1).copy()).pin_memory()
     ring = [torch.empty(slab_elems, dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -503,7 +549,8 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "kernel": "bcast_tile_kernel<float,MUL,16B,8,4>", "launch_ms": launch_ms, "peak_source": peak_src},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 4 * (ROWS_PER_RANK * D + D * D),
-                "d2h_bytes_per_step": 4 * ROWS_PER_RANK * D * D, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                "d2h_bytes_per_step": 4 * ROWS_PER_RANK * D * D, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                "host_numa_node": numa_node},
         "gpu_launches": int(launches), "clocks": clocks,
     }
 
@@ -528,6 +575,15 @@ def main():
         line["cpu_baseline"] = {"value": n * SLAB_BYTES / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"{n} slabs of out[16,4096,4096]: materialise a and b, then the reference Mul (tensor.rs:435-446)",
                                 "seconds": dt, "host_cores_available": os.cpu_count()}
+        am = oracle.fill_uniform("f32", SLAB_ROWS * D, SEED + 2, 0, -1.0, 1.0).reshape(SLAB_ROWS, 1, D)
+        bm = oracle.fill_uniform("f32", D * D, SEED + 3, 0, -1.0, 1.0).reshape(1, D, D)
+        t0 = time.perf_counter()
+        _ = am * bm  # numpy broadcasting, courtesy second baseline
+        line["cpu_baseline"]["numpy_value"] = SLAB_BYTES / (time.perf_counter() - t0) / 1e9
+        try:
+            line["cpu_baseline"]["config1_ms"] = cpu_config1(oracle, np)
+        except Exception as e:
+            line["cpu_baseline"]["config1_ms"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
