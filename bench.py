@@ -571,10 +571,21 @@ def main():
         except Exception as e:  # the headline line must still be printed
             line["suite"] = {"error": repr(e)}
     if world > 1 and not args.no_suite:
+        # The sharded suite is extra: whatever happens in it (a peer that cannot map the IPC windows, an exchange kernel that
+        # times out), the headline line measured above must still come out.  A watchdog prints it and ends the process.
+        def bail():
+            if rank == 0:
+                line["suite_sharded"] = {"error": "timed out after 240 s"}
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        dog = threading.Timer(240.0, bail)
+        dog.daemon = True
+        dog.start()
         try:
             sharded_suite = run_suite_sharded(torch, dist, feo, ctx, rank, world, hbm_peak)
-        except Exception as e:  # collective code: every rank runs it; the headline line must still be printed
+        except Exception as e:  # collective code: every rank runs it
             sharded_suite = {"error": repr(e)}
+        dog.cancel()
         line["suite_sharded"] = sharded_suite
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import feo_oracle as oracle  # checker / baseline only: never on the measured GPU path
