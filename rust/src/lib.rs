@@ -13,6 +13,7 @@
 //! let s = (a + b).sum(vec![0, 2]);          // one elementwise kernel, one reduction; operands are consumed
 //! let host: Vec<f32> = s.to_vec();
 //! ```
+pub mod comm;
 pub mod context;
 pub mod device_matrix;
 pub mod device_storage;
@@ -20,6 +21,7 @@ pub mod device_tensor;
 pub mod device_vector;
 pub mod ffi;
 
+pub use comm::{PeerComm, PeerHandle, PeerWindow};
 pub use context::Context;
 pub use device_matrix::DeviceMatrix;
 pub use device_storage::{DeviceElem, DeviceStorage};
