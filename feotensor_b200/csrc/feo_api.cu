@@ -7,6 +7,7 @@
 #include "feo_common.cuh"
 
 int feo_fail(feo_ctx *ctx, int status, const char *fmt, ...) {
+    FEO_ENTER(ctx);
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -41,6 +42,7 @@ cudaError_t feo_alloc_async(feo_ctx *ctx, void **ptr, size_t bytes) {
 }
 
 int feo_side_stream(feo_ctx *ctx) {
+    FEO_ENTER(ctx);
     if (ctx->side_stream) return FEO_OK;
     int lo = 0, hi = 0;
     FEO_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -51,6 +53,7 @@ int feo_side_stream(feo_ctx *ctx) {
 }
 
 int feo_workspace(feo_ctx *ctx, size_t bytes, void **ptr) {
+    FEO_ENTER(ctx);
     if (bytes > ctx->workspace_bytes) {
         if (ctx->workspace) FEO_CUDA(ctx, cudaFreeAsync(ctx->workspace, ctx->stream));
         ctx->workspace = nullptr;
@@ -120,6 +123,7 @@ int feo_init(int device, feo_ctx **out) {
 }
 
 int feo_shutdown(feo_ctx *ctx) {
+    FEO_ENTER(ctx);
     if (!ctx) return FEO_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -139,6 +143,7 @@ int feo_shutdown(feo_ctx *ctx) {
 const char *feo_last_error(feo_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 
 int feo_set_stream(feo_ctx *ctx, void *s) {
+    FEO_ENTER(ctx);
     if (!ctx) return FEO_ERR_SHAPE;
     // the workspace was allocated stream-ordered on the old stream: settle it before switching
     FEO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -147,6 +152,7 @@ int feo_set_stream(feo_ctx *ctx, void *s) {
 }
 void *feo_get_stream(feo_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 int feo_sync(feo_ctx *ctx) {
+    FEO_ENTER(ctx);
     FEO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FEO_OK;
 }
@@ -158,44 +164,53 @@ int feo_tune(feo_ctx *ctx, int knob, int value) {
 }
 
 int feo_malloc(feo_ctx *ctx, size_t bytes, void **dptr) {
+    FEO_ENTER(ctx);
     if (!dptr) return feo_fail(ctx, FEO_ERR_SHAPE, "null output pointer");
     *dptr = nullptr;
     FEO_CUDA(ctx, feo_alloc_async(ctx, dptr, bytes ? bytes : 1));
     return FEO_OK;
 }
 int feo_free(feo_ctx *ctx, void *dptr) {
+    FEO_ENTER(ctx);
     if (dptr) FEO_CUDA(ctx, cudaFreeAsync(dptr, ctx->stream));  // stream-ordered: takes effect after every earlier kernel
     return FEO_OK;
 }
 int feo_trim(feo_ctx *ctx) {
+    FEO_ENTER(ctx);
     if (!ctx) return FEO_ERR_SHAPE;
     FEO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->pool) FEO_CUDA(ctx, cudaMemPoolTrimTo(ctx->pool, 0));
     return FEO_OK;
 }
 int feo_host_alloc(feo_ctx *ctx, size_t bytes, void **hptr) {
+    FEO_ENTER(ctx);
     FEO_CUDA(ctx, cudaMallocHost(hptr, bytes ? bytes : 1));
     return FEO_OK;
 }
 int feo_host_free(feo_ctx *ctx, void *hptr) {
+    FEO_ENTER(ctx);
     if (hptr) FEO_CUDA(ctx, cudaFreeHost(hptr));
     return FEO_OK;
 }
 int feo_upload(feo_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    FEO_ENTER(ctx);
     if (bytes) FEO_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return FEO_OK;
 }
 int feo_download_async(feo_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    FEO_ENTER(ctx);
     if (bytes) FEO_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return FEO_OK;
 }
 int feo_download(feo_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    FEO_ENTER(ctx);
     int rc = feo_download_async(ctx, dst, src, bytes);
     if (rc != FEO_OK) return rc;
     FEO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FEO_OK;
 }
 int feo_copy(feo_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    FEO_ENTER(ctx);
     if (bytes) FEO_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return FEO_OK;
 }
@@ -249,10 +264,12 @@ int feo_reduce_divisor(int dtype, int rank, const size_t *shape, int naxes, cons
 
 // ---- constructors --------------------------------------------------------------------------------
 int feo_fill(feo_ctx *ctx, int dtype, void *out, const void *value, size_t n) {
+    FEO_ENTER(ctx);
     if (!ctx || !out || !value) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     return feo_impl_fill(ctx, dtype, out, value, n);
 }
 int feo_eye(feo_ctx *ctx, int dtype, void *out, size_t rows, size_t cols) {
+    FEO_ENTER(ctx);
     if (!ctx || !out) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     if (rows == 0 || cols == 0) return feo_fail(ctx, FEO_ERR_SHAPE, "Dimension cannot be zero");
     if (rows > cols) return feo_fail(ctx, FEO_ERR_SHAPE, "out of bounds for dimension 1");  // matrix.rs:38-40
@@ -260,6 +277,7 @@ int feo_eye(feo_ctx *ctx, int dtype, void *out, size_t rows, size_t cols) {
 }
 
 int feo_fill_uniform(feo_ctx *ctx, int dtype, void *out, size_t n, uint64_t seed, uint64_t first_index, double lo, double hi) {
+    FEO_ENTER(ctx);
     if (!ctx || !out) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     if (!(hi > lo)) return feo_fail(ctx, FEO_ERR_SHAPE, "fill_uniform needs hi > lo");
     if (n == 0) return FEO_OK;
@@ -268,18 +286,21 @@ int feo_fill_uniform(feo_ctx *ctx, int dtype, void *out, size_t n, uint64_t seed
 
 // ---- elementwise ---------------------------------------------------------------------------------
 int feo_ewise(feo_ctx *ctx, int op, int dtype, void *out, const void *a, const void *b, size_t n) {
+    FEO_ENTER(ctx);
     if (!ctx || !out || !a || !b) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     if (op < FEO_ADD || op > FEO_DIV) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "unknown op %d", op);
     if (n == 0) return FEO_OK;
     return feo_impl_ewise(ctx, op, dtype, out, a, b, nullptr, n);
 }
 int feo_ewise_scalar(feo_ctx *ctx, int op, int dtype, void *out, const void *a, const void *scalar_host, size_t n) {
+    FEO_ENTER(ctx);
     if (!ctx || !out || !a || !scalar_host) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     if (op < FEO_ADD || op > FEO_DIV) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "unknown op %d", op);
     if (n == 0) return FEO_OK;
     return feo_impl_ewise(ctx, op, dtype, out, a, nullptr, scalar_host, n);
 }
 int feo_pow(feo_ctx *ctx, int dtype, void *out, const void *a, const void *power_host, size_t n) {
+    FEO_ENTER(ctx);
     if (!ctx || !out || !a || !power_host) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     if (dtype != FEO_F32 && dtype != FEO_F64) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "pow needs a Float element type (tensor.rs:325)");
     if (n == 0) return FEO_OK;
@@ -287,6 +308,7 @@ int feo_pow(feo_ctx *ctx, int dtype, void *out, const void *a, const void *power
 }
 int feo_ewise_broadcast(feo_ctx *ctx, int op, int dtype, void *out, const void *a, const void *b, int rank,
                         const size_t *shape, const size_t *sa, const size_t *sb) {
+    FEO_ENTER(ctx);
     if (!ctx || !out || !a || !b) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     if (op < FEO_ADD || op > FEO_DIV) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "unknown op %d", op);
     if (rank < 0 || rank > FEO_MAX_RANK) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "rank %d > %d", rank, FEO_MAX_RANK);
@@ -294,6 +316,7 @@ int feo_ewise_broadcast(feo_ctx *ctx, int op, int dtype, void *out, const void *
     return feo_impl_broadcast(ctx, op, dtype, out, a, b, rank, shape, sa, sb);
 }
 int feo_arith_flag(feo_ctx *ctx, int *flag, int clear) {
+    FEO_ENTER(ctx);
     int v = 0;
     FEO_CUDA(ctx, cudaMemcpyAsync(&v, ctx->arith_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     FEO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -315,12 +338,14 @@ static int reduce_args(feo_ctx *ctx, int kind, void *out, const void *in, int ra
 }
 int feo_reduce(feo_ctx *ctx, int kind, int dtype, void *out, const void *in, int rank, const size_t *shape, int naxes,
                const size_t *axes) {
+    FEO_ENTER(ctx);
     int rc = reduce_args(ctx, kind, out, in, rank, shape, naxes, axes);
     if (rc != FEO_OK) return rc;
     return feo_impl_reduce(ctx, kind, dtype, out, in, nullptr, rank, shape, naxes, axes, 0);
 }
 int feo_reduce_partial(feo_ctx *ctx, int kind, int dtype, void *out, const void *in, int rank, const size_t *shape,
                        int naxes, const size_t *axes) {
+    FEO_ENTER(ctx);
     int rc = reduce_args(ctx, kind, out, in, rank, shape, naxes, axes);
     if (rc != FEO_OK) return rc;
     if (kind == FEO_VAR && dtype != FEO_F32 && dtype != FEO_F64)
@@ -329,6 +354,7 @@ int feo_reduce_partial(feo_ctx *ctx, int kind, int dtype, void *out, const void 
 }
 int feo_reduce_sqdev(feo_ctx *ctx, int dtype, void *out, const void *in, const void *mean, int rank, const size_t *shape,
                      int naxes, const size_t *axes) {
+    FEO_ENTER(ctx);
     int rc = reduce_args(ctx, FEO_SUM, out, in, rank, shape, naxes, axes);
     if (rc != FEO_OK) return rc;
     if (!mean) return feo_fail(ctx, FEO_ERR_SHAPE, "null mean");
@@ -336,6 +362,7 @@ int feo_reduce_sqdev(feo_ctx *ctx, int dtype, void *out, const void *in, const v
 }
 int feo_var_merge(feo_ctx *ctx, int dtype, void *out, const void *partials, size_t nparts, size_t nout, size_t count_per_part,
                   const void *divisor_host) {
+    FEO_ENTER(ctx);
     if (!ctx || !out || !partials || !divisor_host) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     if (dtype != FEO_F32 && dtype != FEO_F64) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "feo_var_merge is float-only");
     if (nparts == 0 || nout == 0) return feo_fail(ctx, FEO_ERR_SHAPE, "empty merge");
@@ -344,32 +371,38 @@ int feo_var_merge(feo_ctx *ctx, int dtype, void *out, const void *partials, size
 
 // ---- products ------------------------------------------------------------------------------------
 int feo_outer(feo_ctx *ctx, int dtype, void *out, const void *a, size_t na, const void *b, size_t nb) {
+    FEO_ENTER(ctx);
     if (!ctx || !out || !a || !b) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     if (na == 0 || nb == 0) return feo_fail(ctx, FEO_ERR_SHAPE, "Dimension cannot be zero");
     const size_t shape[2] = {na, nb}, sa[2] = {1, 0}, sb[2] = {0, 1};
     return feo_impl_broadcast(ctx, FEO_MUL, dtype, out, a, b, 2, shape, sa, sb);
 }
 int feo_dot(feo_ctx *ctx, int dtype, void *out, const void *a, const void *b, size_t n) {
+    FEO_ENTER(ctx);
     if (!ctx || !out || !a || !b) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     if (n == 0) return feo_fail(ctx, FEO_ERR_SHAPE, "Dimension cannot be zero");
     return feo_impl_dotlike(ctx, 1, dtype, out, a, b, 1, n);
 }
 int feo_dot_batched(feo_ctx *ctx, int dtype, void *out, const void *a, const void *b, size_t batch, size_t n) {
+    FEO_ENTER(ctx);
     if (!ctx || !out || !a || !b) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     if (n == 0 || batch == 0) return feo_fail(ctx, FEO_ERR_SHAPE, "Dimension cannot be zero");
     return feo_impl_dotlike(ctx, 1, dtype, out, a, b, batch, n);
 }
 int feo_matvec(feo_ctx *ctx, int dtype, void *out, const void *A, const void *v, size_t M, size_t K) {
+    FEO_ENTER(ctx);
     if (!ctx || !out || !A || !v) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     if (M == 0 || K == 0) return feo_fail(ctx, FEO_ERR_SHAPE, "Dimension cannot be zero");
     return feo_impl_dotlike(ctx, 2, dtype, out, A, v, M, K);
 }
 int feo_vecmat(feo_ctx *ctx, int dtype, void *out, const void *v, const void *A, size_t K, size_t N) {
+    FEO_ENTER(ctx);
     if (!ctx || !out || !A || !v) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     if (N == 0 || K == 0) return feo_fail(ctx, FEO_ERR_SHAPE, "Dimension cannot be zero");
     return feo_impl_dotlike(ctx, 3, dtype, out, A, v, K, N);
 }
 int feo_matmul(feo_ctx *ctx, int algo, int dtype, void *C, const void *A, const void *B, size_t M, size_t K, size_t N) {
+    FEO_ENTER(ctx);
     if (!ctx || !C || !A || !B) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     if (M == 0 || K == 0 || N == 0) return feo_fail(ctx, FEO_ERR_SHAPE, "Dimension cannot be zero");
     if (algo == FEO_MATMUL_AUTO)

@@ -52,6 +52,13 @@ struct feo_ctx {
 };
 
 int feo_fail(feo_ctx *ctx, int status, const char *fmt, ...);
+// Every entry point makes the context's device current first: a process may hold contexts on several devices (and the host
+// framework may have switched devices since the last call).  cudaSetDevice on the already-current device is a cheap no-op.
+#define FEO_ENTER(c)                                   \
+    do {                                               \
+        feo_ctx *c_ = (c);                             \
+        if (c_) cudaSetDevice(c_->device);             \
+    } while (0)
 // True if the launch described by ctx->pending may start before the kernels in the window have finished (no RAW / WAR /
 // WAW overlap with any of them, window not full); records it.  False: launch normally (full stream order).
 bool feo_pdl_admit(feo_ctx *ctx);

@@ -434,10 +434,11 @@ namespace {
 int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const feo_peer::BParts *parts, const feo_peer::XchgParams *sync,
                       size_t M, size_t K, size_t N) {
     if (!feo_aligned16(A) || !feo_aligned16(C) || (B && !feo_aligned16(B))) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "TF32X3 needs 16-byte aligned operands");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // the opt-in is per device
+    const int dev = ctx->device & 63;
+    if (!attr_set[dev]) {
         FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     // workspace: A_hi | A_lo [M,Kp]  and  Bt_hi | Bt_lo [N,Kp], Kp = K rounded up to one k-block
     const size_t Kp = (K + BK - 1) / BK * BK;

@@ -40,6 +40,7 @@ template <typename T, int KIND> __device__ __forceinline__ T combine2(T a, T b) 
 template <typename T, int KIND, int V>
 __global__ void __launch_bounds__(kXThreads) xchg_allreduce_kernel(const __grid_constant__ XchgParams p, T *__restrict__ out, T divisor,
                                                                    T count, int *arith_flag) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the local partial in front of this launch is complete and visible
     signal_and_wait(p);
     using Vec = AVec<T, V>;
     const long long nv = p.n / V;
@@ -104,10 +105,22 @@ int launch_allreduce(feo_comm *comm, const XchgParams &p, void *out, size_t n, s
     constexpr int V = 16 / (int)sizeof(T);
     const size_t units = vec ? n / V : n;
     const unsigned blocks = (unsigned)std::min<size_t>(std::max<size_t>(feo_ceil_div(units, (size_t)kXThreads), 1), (size_t)ctx->sm_count * 4);
-    if (vec)
-        xchg_allreduce_kernel<T, KIND, V><<<blocks, kXThreads, 0, ctx->stream>>>(p, (T *)out, divisor, (T)count, ctx->arith_flag);
-    else
-        xchg_allreduce_kernel<T, KIND, 1><<<blocks, kXThreads, 0, ctx->stream>>>(p, (T *)out, divisor, (T)count, ctx->arith_flag);
+    // programmatic dependent launch: the exchange kernel is set up while the local reduction in front of it still runs and
+    // starts the moment that one finishes (it executes griddepcontrol.wait before touching the partial)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(kXThreads);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ctx->knobs[FEO_KNOB_PDL] == 1 ? 0 : 1;
+    T *o = (T *)out;
+    const T cnt = (T)count;
+    int *flag = ctx->arith_flag;
+    if (vec) FEO_CUDA(ctx, cudaLaunchKernelEx(&cfg, xchg_allreduce_kernel<T, KIND, V>, p, o, divisor, cnt, flag));
+    else FEO_CUDA(ctx, cudaLaunchKernelEx(&cfg, xchg_allreduce_kernel<T, KIND, 1>, p, o, divisor, cnt, flag));
     FEO_LAUNCH_CHECK(ctx);
     return FEO_OK;
 }
@@ -141,6 +154,7 @@ XchgParams next_exchange(feo_comm *comm, long long n) {
 extern "C" {
 
 int feo_peer_alloc(feo_ctx *ctx, size_t bytes, void **dptr) {
+    FEO_ENTER(ctx);
     if (!ctx || !dptr || bytes == 0) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     FEO_CUDA(ctx, cudaSetDevice(ctx->device));
     FEO_CUDA(ctx, cudaMalloc(dptr, bytes));  // not the stream-ordered pool: legacy IPC handles need a plain allocation
@@ -149,12 +163,14 @@ int feo_peer_alloc(feo_ctx *ctx, size_t bytes, void **dptr) {
     return FEO_OK;
 }
 int feo_peer_free(feo_ctx *ctx, void *dptr) {
+    FEO_ENTER(ctx);
     if (!ctx) return FEO_ERR_SHAPE;
     FEO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     FEO_CUDA(ctx, cudaFree(dptr));
     return FEO_OK;
 }
 int feo_peer_export(feo_ctx *ctx, void *dptr, unsigned char *handle) {
+    FEO_ENTER(ctx);
     if (!ctx || !dptr || !handle) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == FEO_PEER_HANDLE_BYTES, "handle size");
     cudaIpcMemHandle_t h;
@@ -163,6 +179,7 @@ int feo_peer_export(feo_ctx *ctx, void *dptr, unsigned char *handle) {
     return FEO_OK;
 }
 int feo_peer_open(feo_ctx *ctx, const unsigned char *handle, void **dptr) {
+    FEO_ENTER(ctx);
     if (!ctx || !dptr || !handle) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, sizeof(h));
@@ -171,6 +188,7 @@ int feo_peer_open(feo_ctx *ctx, const unsigned char *handle, void **dptr) {
     return FEO_OK;
 }
 int feo_peer_close(feo_ctx *ctx, void *dptr) {
+    FEO_ENTER(ctx);
     if (!ctx || !dptr) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     FEO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     FEO_CUDA(ctx, cudaIpcCloseMemHandle(dptr));
@@ -178,6 +196,7 @@ int feo_peer_close(feo_ctx *ctx, void *dptr) {
 }
 
 int feo_comm_create(feo_ctx *ctx, int rank, int world, void *const *windows, size_t window_bytes, feo_comm **out) {
+    FEO_ENTER(ctx);
     if (!ctx || !windows || !out) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
         return feo_fail(ctx, FEO_ERR_SHAPE, "rank %d of %d: at most %d peers (one node)", rank, world, kMaxPeers);
@@ -200,12 +219,14 @@ int feo_comm_destroy(feo_comm *comm) {
     return FEO_OK;
 }
 int feo_comm_slot(feo_comm *comm, void **dptr, size_t *bytes) {
+    FEO_ENTER(comm ? comm->ctx : nullptr);
     if (!comm || !dptr) return FEO_ERR_SHAPE;
     *dptr = static_cast<char *>(comm->windows[comm->rank]) + kFlagBytes + ((comm->epoch + 1) & 1) * comm->slot_bytes;
     if (bytes) *bytes = comm->slot_bytes;
     return FEO_OK;
 }
 int feo_comm_barrier(feo_comm *comm) {
+    FEO_ENTER(comm ? comm->ctx : nullptr);
     if (!comm) return FEO_ERR_SHAPE;
     feo_ctx *ctx = comm->ctx;
     const XchgParams p = next_exchange(comm, 0);
@@ -214,6 +235,7 @@ int feo_comm_barrier(feo_comm *comm) {
     return FEO_OK;
 }
 int feo_comm_allreduce(feo_comm *comm, int kind, int dtype, void *out, size_t n, size_t count_per_rank, const void *divisor_host) {
+    FEO_ENTER(comm ? comm->ctx : nullptr);
     if (!comm || !out) return FEO_ERR_SHAPE;
     feo_ctx *ctx = comm->ctx;
     if (n == 0) return feo_fail(ctx, FEO_ERR_SHAPE, "empty exchange");
@@ -231,6 +253,7 @@ int feo_comm_allreduce(feo_comm *comm, int kind, int dtype, void *out, size_t n,
 // `shape` is the LOCAL block, `divisor_host` the reference's counted-in-T divisor of the GLOBAL shape (feo_reduce_divisor).
 int feo_reduce_sharded(feo_comm *comm, int kind, int dtype, void *out, const void *in, int rank, const size_t *shape, int naxes,
                        const size_t *axes, const void *divisor_host) {
+    FEO_ENTER(comm ? comm->ctx : nullptr);
     if (!comm || !out || !in || !shape) return FEO_ERR_SHAPE;
     feo_ctx *ctx = comm->ctx;
     if (naxes < 1 || !axes || axes[0] != 0) return feo_fail(ctx, FEO_ERR_SHAPE, "the leading (sharded) axis must be reduced; otherwise no exchange is needed");
@@ -263,6 +286,7 @@ int feo_reduce_sharded(feo_comm *comm, int kind, int dtype, void *out, const voi
 
 // Vector::vecmul (vector.rs:71-78) on two identically sharded vectors: `batch` partial dots into the window, then the sum.
 int feo_dot_sharded(feo_comm *comm, int dtype, void *out, const void *a, const void *b, size_t batch, size_t n_local) {
+    FEO_ENTER(comm ? comm->ctx : nullptr);
     if (!comm || !out) return FEO_ERR_SHAPE;
     feo_ctx *ctx = comm->ctx;
     void *slot = nullptr;
@@ -276,6 +300,7 @@ int feo_dot_sharded(feo_comm *comm, int dtype, void *out, const void *a, const v
 
 // All-gather of equally sized parts that live in peer-mapped memory (parts[r] = rank r's buffer as mapped HERE).
 int feo_comm_gather(feo_comm *comm, void *out, const void *const *parts, size_t bytes_per_part) {
+    FEO_ENTER(comm ? comm->ctx : nullptr);
     if (!comm || !out || !parts) return FEO_ERR_SHAPE;
     feo_ctx *ctx = comm->ctx;
     if (bytes_per_part == 0 || bytes_per_part % 4 != 0) return feo_fail(ctx, FEO_ERR_SHAPE, "parts must be a positive multiple of 4 bytes");
@@ -302,6 +327,7 @@ int feo_comm_gather(feo_comm *comm, void *out, const void *const *parts, size_t 
 // A closing barrier keeps every rank's panel untouched until all ranks have read it.
 int feo_matmul_sharded_b(feo_comm *comm, int algo, int dtype, void *C, const void *A, const void *const *b_parts, size_t M, size_t K,
                          size_t N) {
+    FEO_ENTER(comm ? comm->ctx : nullptr);
     if (!comm || !C || !A || !b_parts) return FEO_ERR_SHAPE;
     feo_ctx *ctx = comm->ctx;
     if (M == 0 || K == 0 || N == 0) return feo_fail(ctx, FEO_ERR_SHAPE, "Dimension cannot be zero");
