@@ -503,6 +503,18 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
 }  // namespace
 
 int feo_impl_matmul_tf32x3(feo_ctx *ctx, void *C, const void *A, const void *B, size_t M, size_t K, size_t N) {
+    // Large products: B's split / transpose pre-pass runs on the side stream and publishes k-blocks while the matmul kernel
+    // is already working on the first ones (the sharded-B machinery with a single, local panel and nothing to wait for).
+    const size_t tiles = feo_ceil_div(N, (size_t)BN) * feo_ceil_div(M, (size_t)BM);
+    if (ctx->knobs[FEO_KNOB_GATHER_OVERLAP] == 2 && tiles >= 2 * (size_t)ctx->sm_count && K >= 1024 && feo_aligned16(B)) {
+        feo_peer::BParts parts{};
+        parts.part[0] = static_cast<const float *>(B);
+        parts.world = 1;
+        parts.rows_per_part = (int)K;
+        feo_peer::XchgParams sync{};
+        sync.world = 1;  // epoch 0: no flags, no wait
+        return matmul_tf32x3_run(ctx, C, A, nullptr, &parts, &sync, M, K, N);
+    }
     return matmul_tf32x3_run(ctx, C, A, B, nullptr, nullptr, M, K, N);
 }
 

@@ -398,6 +398,56 @@ def test_reduction_split_counts_agree(feo, oracle):
         ctx.tune(L.KNOB_REDUCE_FUSE, 0)
 
 
+def test_outputs_stay_inside_their_buffers(feo, oracle):
+    """Every kernel family writes exactly its output: the result sits between two canary bands in a larger device buffer
+    (and the operands sit at the very end of theirs, so a read past them would at least pick up the next allocation)."""
+    import feotensor_b200._lib as L
+    ctx = feo.Context.default()
+    lib, h, vp = ctx.lib, ctx.handle, C.c_void_p
+    rng = np.random.default_rng(77)
+    PAD = 64  # elements; keeps 16-byte alignment for every dtype
+
+    def guarded(n, dt):
+        buf = feo.Tensor.fill(feo.shape(n + 2 * PAD), 77, dtype=dt)
+        return buf, buf.data.ptr + PAD * np.dtype(oracle.NP_DTYPES[dt]).itemsize
+
+    def check(buf, n, want, msg):
+        got = buf.to_numpy()
+        np.testing.assert_array_equal(got[:PAD], 77, err_msg=msg + " (wrote before the output)")
+        np.testing.assert_array_equal(got[PAD + n:], 77, err_msg=msg + " (wrote past the output)")
+        return got[PAD:PAD + n]
+
+    for dt in ("f32", "i64"):
+        code = L.code_of(dt)
+        for shape, axes in REDUCE_CASES:
+            x = rand(oracle, rng, dt, shape)
+            t = feo.Tensor(feo.Shape(shape), x)
+            for kind in ("sum", "var", "max"):
+                want = oracle.reduce(kind, x, axes).reshape(-1)
+                buf, optr = guarded(want.size, dt)
+                ctx.check(lib.feo_reduce(h, L.KIND_CODES[kind], code, vp(optr), vp(t.data.ptr), len(shape), L.sizes(shape), len(axes), L.sizes(axes)))
+                got = check(buf, want.size, want, f"reduce {dt} {kind} {shape} {axes}")
+                if dt == "i64" or kind == "max":
+                    np.testing.assert_array_equal(got, want)
+        for sa, sb in BCAST_CASES:
+            a = rand(oracle, rng, dt, sa)
+            b = (np.abs(rand(oracle, rng, dt, sb)) + 1).astype(a.dtype)
+            want = oracle.ewise_broadcast("mul", a, b)
+            ta, tb = feo.Tensor(feo.Shape(sa), a), feo.Tensor(feo.Shape(sb), b)
+            oshape = list(want.shape)
+
+            def strides(src):
+                st, run = [0] * len(src), 1
+                for d in range(len(src) - 1, -1, -1):
+                    st[d] = run if src[d] != 1 or oshape[d] == 1 else 0
+                    run *= src[d]
+                return st
+            buf, optr = guarded(want.size, dt)
+            ctx.check(lib.feo_ewise_broadcast(h, L.MUL, code, vp(optr), vp(ta.data.ptr), vp(tb.data.ptr), len(oshape), L.sizes(oshape),
+                                              L.sizes(strides(sa)), L.sizes(strides(sb))))
+            np.testing.assert_array_equal(check(buf, want.size, want, f"bcast {dt} {sa} {sb}"), want.reshape(-1))
+
+
 def test_many_group_reductions_multipass_and_generic_agree(feo, oracle):
     """More than four alternating kept / reduced groups: the multi-pass route (sum / mean / max / min) and the
     one-kernel generic fallback (knob REDUCE_SPLIT = -1; always used for var) give the oracle's integers bit for bit."""

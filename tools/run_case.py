@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--pdl", type=int, default=0, help="1 = disable programmatic dependent launch")
     ap.add_argument("--slabs", type=int, default=1)
     ap.add_argument("--nofuse", type=int, default=0, help="1 = two-launch combine for split reductions")
+    ap.add_argument("--overlap", type=int, default=0, help="FEO_KNOB_GATHER_OVERLAP (2 = overlapped B pre-pass on one GPU)")
     ap.add_argument("--l2keep", type=int, default=0, help="1 = disable the evict_last policy on broadcast operands")
     args = ap.parse_args()
 
@@ -58,6 +59,7 @@ def main():
     ctx.tune(L.KNOB_PDL, args.pdl)
     ctx.tune(L.KNOB_REDUCE_FUSE, args.nofuse)
     ctx.tune(L.KNOB_BCAST_L2KEEP, args.l2keep)
+    ctx.tune(L.KNOB_GATHER_OVERLAP, args.overlap)
     lib, h, vp = ctx.lib, ctx.handle, C.c_void_p
     dt = L.code_of(args.dtype)
     es = L.np_dtype(args.dtype).itemsize
