@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, 3) reduce_cols_kernel(T *__restrict_
                                                                const T *__restrict__ aux, const __grid_constant__ Geom G,
                                                                T divisor, int *flag) {
     constexpr int W = VEC ? VecN<T>::value : 1;
-    constexpr int U = 8;
+    constexpr int U = (VEC || J > 1) ? 8 : 16;  // 4-byte loads: twice the rows in flight, half the Welford merges per element
     using V = AVec<T, W>;
     long long blk = blockIdx.x;
     const long long bx = blk % G.xblocks; blk /= G.xblocks;
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 3) reduce_cols_kernel(T *__restrict_
             }
     }
     // fewer than U rows left (or, with few rows in all, the whole job): TU rows x J columns of loads go out together
-    constexpr int TU = (J == 1) ? 4 : 2;
+    constexpr int TU = (J == 1 || !VEC) ? 4 : 2;
     for (; r < r_hi; r += TU) {
         const int nrem = (int)((r_hi - r < TU) ? r_hi - r : TU);
         V v[J][TU];
@@ -375,17 +375,28 @@ __global__ void __launch_bounds__(kThreads, 3) reduce_cols_kernel(T *__restrict_
                 for (int u = 0; u < TU; ++u)
                     if (u < nrem) v[j][u] = ld_stream(reinterpret_cast<const V *>(base + (r + u) * G.K2) + (long long)j * kThreads);
             }
+        T w[TU];
 #pragma unroll
-        for (int u = 0; u < TU; ++u)
-            if (u < nrem) {
-                T w = (T)1;
-                if constexpr (LOADER == LD_VECMAT) w = __ldg(in2 + r + u);
+        for (int u = 0; u < TU; ++u) {
+            w[u] = (T)1;
+            if constexpr (LOADER == LD_VECMAT) { if (u < nrem) w[u] = __ldg(in2 + r + u); }
+        }
 #pragma unroll
-                for (int j = 0; j < J; ++j)
-                    if (live[j]) {
+        for (int j = 0; j < J; ++j)
+            if (live[j]) {
 #pragma unroll
-                        for (int k = 0; k < W; ++k) acc[j][k].push(LOADER == LD_VECMAT ? w_mul(w, v[j][u].v[k]) : v[j][u].v[k]);
+                for (int k = 0; k < W; ++k) {
+                    T x[TU];
+#pragma unroll
+                    for (int u = 0; u < TU; ++u) x[u] = (u < nrem) ? (LOADER == LD_VECMAT ? w_mul(w[u], v[j][u].v[k]) : v[j][u].v[k]) : (T)0;
+                    if constexpr (KIND == K_WELFORD) {
+                        acc[j][k].push_masked(x, nrem);  // one division per chunk, not one per element
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < TU; ++u)
+                            if (u < nrem) acc[j][k].push(x[u]);
                     }
+                }
             }
     }
     if (VEC && G.S <= 1 && G.fin != FIN_MEAN_M2) {
