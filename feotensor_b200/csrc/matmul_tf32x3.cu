@@ -54,9 +54,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded wait: a pipeline bug traps (and reports) instead of hanging the GPU.
+// Bounded wait: a pipeline bug traps (and reports) after 30 s instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int what) {
     const uint32_t addr = smem_u32(bar);
+    unsigned long long t_start = 0;
     for (uint32_t spin = 0;; ++spin) {
         uint32_t done;
         asm volatile(
@@ -67,10 +68,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int wh
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) return;
-        if (spin > 20000000u) {
-            printf("matmul_tf32x3: mbarrier wait timed out (what=%d block=%d,%d thread=%d parity=%u)\n", what, blockIdx.x, 0,
-                   threadIdx.x, parity);
-            __trap();
+        // With B arriving from other GPUs the pipeline legitimately waits for a late peer, so the bound is wall time
+        // (the same 30 s as the exchange flags), sampled every 2^20 polls.
+        if ((spin & 0xFFFFFu) == 0xFFFFFu) {
+            if (t_start == 0) t_start = feo_peer::global_ns();
+            else if (feo_peer::global_ns() - t_start > feo_peer::kWaitNs) {
+                printf("matmul_tf32x3: mbarrier wait timed out (what=%d block=%d thread=%d parity=%u)\n", what, blockIdx.x, threadIdx.x, parity);
+                __trap();
+            }
         }
     }
 }

@@ -18,6 +18,9 @@ import numpy as np
 # Lazy module loading synchronises the context the first time a kernel is launched; with one rank's exchange kernel already
 # spinning for the others that would deadlock this single-process arrangement (separate processes are not affected).
 os.environ["CUDA_MODULE_LOADING"] = "EAGER"
+# Each rank uses two streams (main + the side stream of the overlapped matmul pre-pass); with more streams than hardware queues
+# (8 by default) a rank's pre-pass can be queued behind another rank's waiting kernel.  Again a single-process artefact.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
