@@ -130,3 +130,25 @@ def test_flatten_reduce_shape_divisor_match_oracle(oracle):
         assert lib.feo_reduce_divisor(L.code_of(dt), len(shape), L.sizes(shape), len(axes), L.sizes(axes),
                                       out.ctypes.data_as(C.c_void_p)) == 0
         assert out[0] == oracle.reduce_divisor(dt, shape, axes), (dt, shape, axes)
+
+
+def test_flat_index_magic_division_is_exact_below_2_31():
+    """The flat-index broadcast kernel (csrc/ewise_impl.cuh: FastDiv) divides 32-bit indices by the collapsed extents with
+    q = (umulhi(n, mul) + n) >> shift.  The host-side constants, restated here, must give floor(n / d) for every n < 2^31
+    (the launcher takes the path only below that), for small, large, power-of-two and awkward divisors."""
+    rng = np.random.default_rng(0)
+
+    def magic(d):
+        sh = 0
+        while sh < 32 and (1 << sh) < d:
+            sh += 1
+        return ((((1 << 32) * ((1 << sh) - d)) // d) + 1) & 0xFFFFFFFF, sh
+
+    divisors = list(range(1, 300)) + [int(x) for x in rng.integers(1, 2 ** 31 - 1, 500)] + [2 ** 31 - 1, 2 ** 30, 2 ** 30 + 1, 4099, 89478485]
+    for d in divisors:
+        mul, sh = magic(d)
+        n = np.concatenate([rng.integers(0, 2 ** 31 - 8, 500, dtype=np.uint64),
+                            np.array([0, 1, d - 1, d, min(d + 1, 2 ** 31 - 8), 2 ** 31 - 9, 2 ** 31 - 8], dtype=np.uint64)])
+        t = (n * np.uint64(mul)) >> np.uint64(32)
+        q = ((t + n) & np.uint64(0xFFFFFFFF)) >> np.uint64(sh)
+        np.testing.assert_array_equal(q, n // np.uint64(d), err_msg=f"d={d}")
