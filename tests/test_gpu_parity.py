@@ -555,7 +555,7 @@ def test_dot_matvec_vecmat(feo, oracle, dt):
             np.testing.assert_array_equal(got.to_numpy(), want)
         else:
             assert_sum_like(got.to_numpy(), want, np.abs(a.astype(np.float64) * b).sum(), n + 1, dt, f"dot n={n}")
-    for m, k in ((1, 1), (7, 5), (33, 1000), (500, 36), (64, 4096)):
+    for m, k in ((1, 1), (7, 5), (33, 1000), (500, 36), (64, 4096), (3, 5000), (2, 4099), (5000, 3)):
         A, v, w = rand(oracle, rng, dt, (m, k)), rand(oracle, rng, dt, k), rand(oracle, rng, dt, m)
         tA = feo.Matrix(feo.shape(m, k), A)
         g1, w1 = tA.vecmul(feo.Vector(v)).to_numpy(), oracle.matvec(A, v)
