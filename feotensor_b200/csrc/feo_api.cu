@@ -348,8 +348,6 @@ int feo_reduce_partial(feo_ctx *ctx, int kind, int dtype, void *out, const void 
     FEO_ENTER(ctx);
     int rc = reduce_args(ctx, kind, out, in, rank, shape, naxes, axes);
     if (rc != FEO_OK) return rc;
-    if (kind == FEO_VAR && dtype != FEO_F32 && dtype != FEO_F64)
-        return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "integer variance is two-pass: use FEO_SUM partials, then feo_reduce_sqdev");
     return feo_impl_reduce(ctx, kind, dtype, out, in, nullptr, rank, shape, naxes, axes, 1);
 }
 int feo_reduce_sqdev(feo_ctx *ctx, int dtype, void *out, const void *in, const void *mean, int rank, const size_t *shape,
@@ -364,7 +362,7 @@ int feo_var_merge(feo_ctx *ctx, int dtype, void *out, const void *partials, size
                   const void *divisor_host) {
     FEO_ENTER(ctx);
     if (!ctx || !out || !partials || !divisor_host) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
-    if (dtype != FEO_F32 && dtype != FEO_F64) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "feo_var_merge is float-only");
+    if (feo_dtype_size(dtype) == 0) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "unsupported dtype %d", dtype);
     if (nparts == 0 || nout == 0) return feo_fail(ctx, FEO_ERR_SHAPE, "empty merge");
     return feo_impl_var_merge(ctx, dtype, out, partials, nparts, nout, count_per_part, divisor_host);
 }

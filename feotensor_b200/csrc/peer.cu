@@ -57,13 +57,22 @@ __global__ void __launch_bounds__(kXThreads) xchg_allreduce_kernel(const __grid_
         Vec res;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            if constexpr (KIND == X_VAR) {
+            if constexpr (KIND == X_VAR && std::is_floating_point<T>::value) {
                 Acc<T, K_WELFORD> acc;
                 acc.init((T)0);
 #pragma unroll
                 for (int r = 0; r < kMaxPeers; ++r)
                     if (r < p.world) acc.merge_raw(count, part[r].v[j], part2[r].v[j]);
                 res.v[j] = acc.m2 / divisor;
+            } else if constexpr (KIND == X_VAR) {  // integers: wrapping S1 | S2 partials, exact by the ring identity (K_SUMSQ)
+                T s1 = (T)0, s2 = (T)0;
+#pragma unroll
+                for (int r = 0; r < kMaxPeers; ++r)
+                    if (r < p.world) { s1 = w_add(s1, part[r].v[j]); s2 = w_add(s2, part2[r].v[j]); }
+                const T m = w_div(s1, divisor, arith_flag);
+                T v = w_sub(s2, w_mul(w_mul((T)2, m), s1));
+                v = w_add(v, w_mul(divisor, w_mul(m, m)));
+                res.v[j] = w_div(v, divisor, arith_flag);
             } else {
                 T a = part[0].v[j];
 #pragma unroll
@@ -131,9 +140,7 @@ template <typename T> int dispatch_kind(feo_comm *comm, int kind, const XchgPara
     case FEO_MEAN: return launch_allreduce<T, X_MEAN>(comm, p, out, n, count, div);
     case FEO_MAX: return launch_allreduce<T, X_MAX>(comm, p, out, n, count, div);
     case FEO_MIN: return launch_allreduce<T, X_MIN>(comm, p, out, n, count, div);
-    case FEO_VAR:
-        if constexpr (std::is_floating_point<T>::value) return launch_allreduce<T, X_VAR>(comm, p, out, n, count, div);
-        else return feo_fail(comm->ctx, FEO_ERR_UNSUPPORTED, "integer variance exchanges sums, not Welford partials");
+    case FEO_VAR: return launch_allreduce<T, X_VAR>(comm, p, out, n, count, div);
     default: return feo_fail(comm->ctx, FEO_ERR_UNSUPPORTED, "unknown reduction kind %d", kind);
     }
 }
@@ -264,24 +271,16 @@ int feo_reduce_sharded(feo_comm *comm, int kind, int dtype, void *out, const voi
     const size_t nout = feo_shape_size(out_rank, out_shape);
     size_t count = 1;
     for (int i = 0; i < naxes; ++i) count *= shape[axes[i]];
-    const bool is_float = dtype == FEO_F32 || dtype == FEO_F64;
     void *slot = nullptr;
     size_t slot_bytes = 0;
     feo_comm_slot(comm, &slot, &slot_bytes);
-    if (nout * feo_dtype_size(dtype) * (kind == FEO_VAR && is_float ? 2 : 1) > slot_bytes)
+    if (nout * feo_dtype_size(dtype) * (kind == FEO_VAR ? 2 : 1) > slot_bytes)
         return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "partial exceeds the %zu-byte slot", slot_bytes);
+    // var partials: floats (mean | M2) merged by Chan, integers (S1 | S2) summed and resolved by the ring identity -- one
+    // pass over the data and one exchange either way
     int rc;
-    if (kind != FEO_VAR || is_float) {
-        if ((rc = feo_reduce_partial(ctx, kind, dtype, slot, in, rank, shape, naxes, axes)) != FEO_OK) return rc;
-        return feo_comm_allreduce(comm, kind, dtype, out, nout, count, divisor_host);
-    }
-    // integers: the reference's two passes, exactly (tensor.rs:171-177, 188, 196-202): global truncated mean, then the
-    // squared deviations from it.  `out` holds the mean between the two exchanges.
-    if ((rc = feo_reduce_partial(ctx, FEO_SUM, dtype, slot, in, rank, shape, naxes, axes)) != FEO_OK) return rc;
-    if ((rc = feo_comm_allreduce(comm, FEO_MEAN, dtype, out, nout, count, divisor_host)) != FEO_OK) return rc;
-    feo_comm_slot(comm, &slot, &slot_bytes);
-    if ((rc = feo_reduce_sqdev(ctx, dtype, slot, in, out, rank, shape, naxes, axes)) != FEO_OK) return rc;
-    return feo_comm_allreduce(comm, FEO_MEAN, dtype, out, nout, count, divisor_host);
+    if ((rc = feo_reduce_partial(ctx, kind, dtype, slot, in, rank, shape, naxes, axes)) != FEO_OK) return rc;
+    return feo_comm_allreduce(comm, kind, dtype, out, nout, count, divisor_host);
 }
 
 // Vector::vecmul (vector.rs:71-78) on two identically sharded vectors: `batch` partial dots into the window, then the sum.

@@ -20,7 +20,7 @@
 namespace feo_red {
 
 constexpr int kThreads = 256;
-enum { K_SUM = 0, K_MAX = 1, K_MIN = 2, K_WELFORD = 3, K_SQDEV = 4, K_INTVAR = 5 };
+enum { K_SUM = 0, K_MAX = 1, K_MIN = 2, K_WELFORD = 3, K_SQDEV = 4, K_INTVAR = 5, K_SUMSQ = 6 };
 enum { FIN_NONE = 0, FIN_DIV = 1, FIN_VAR = 2, FIN_MEAN_M2 = 3 };
 enum { LD_PLAIN = 0, LD_MUL = 1, LD_MATVEC = 2, LD_VECMAT = 3 };
 
@@ -130,6 +130,22 @@ template <typename T> struct Acc<T, K_INTVAR> {
         v = q;
     }
 };
+// Integer variance in ONE pass for any geometry.  The reference's two passes (tensor.rs:171-177, 188-202) are wrapping
+// integer arithmetic, i.e. arithmetic in the ring Z / 2^k, where  sum (x - m)^2 = sum x^2 - 2 m sum x + n m^2  holds exactly
+// whatever overflows on the way.  So the wrapping sum and sum of squares determine the reference's result bit for bit:
+// m = S1 / n (truncating, on the wrapped S1 like the reference's own mean), var = (S2 - 2 m S1 + n m^2) / n.
+template <typename T> struct Acc<T, K_SUMSQ> {
+    T v, q;
+    __device__ __forceinline__ void init(T) { v = (T)0; q = (T)0; }
+    __device__ __forceinline__ void push(T x) { v = w_add(v, x); q = w_add(q, w_mul(x, x)); }
+    __device__ __forceinline__ void merge(const Acc &o) { v = w_add(v, o.v); q = w_add(q, o.q); }
+    template <int N> __device__ __forceinline__ void push_batch(const T (&x)[N]) {
+        T s = (T)0, t = (T)0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { s = w_add(s, x[i]); t = w_add(t, w_mul(x[i], x[i])); }
+        v = w_add(v, s); q = w_add(q, t);
+    }
+};
 // Welford / Chan: (count, mean, M2).  Batches are combined two-pass in registers and merged with one
 // division per batch, so the per-element cost stays ~4 flops while keeping Welford's stability.
 template <typename T> struct Acc<T, K_WELFORD> {
@@ -193,6 +209,8 @@ template <typename T, int KIND> __device__ __forceinline__ Acc<T, KIND> shfl_dow
         r.v = shfl_down_t(a.v, off); r.m = a.m;
     } else if constexpr (KIND == K_INTVAR) {
         r.v = shfl_down_t(a.v, off); r.n = a.n;
+    } else if constexpr (KIND == K_SUMSQ) {
+        r.v = shfl_down_t(a.v, off); r.q = shfl_down_t(a.q, off);
     } else {
         r.v = shfl_down_t(a.v, off);
     }
@@ -208,6 +226,12 @@ __device__ __forceinline__ void finalize(const Acc<T, KIND> &acc, T *out, long l
     if constexpr (KIND == K_WELFORD) {
         if (fin == FIN_MEAN_M2) { out[o] = acc.mean; out[nout + o] = acc.m2; }
         else out[o] = acc.m2 / divisor;
+    } else if constexpr (KIND == K_SUMSQ) {
+        if (fin == FIN_MEAN_M2) { out[o] = acc.v; out[nout + o] = acc.q; return; }  // partial: S1 | S2
+        const T m = w_div(acc.v, divisor, flag);
+        T v = w_sub(acc.q, w_mul(w_mul((T)2, m), acc.v));
+        v = w_add(v, w_mul(divisor, w_mul(m, m)));
+        out[o] = w_div(v, divisor, flag);
     } else {
         T v = acc.v;
         if (fin == FIN_DIV) v = w_div(v, divisor, flag);
@@ -399,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 3) reduce_cols_kernel(T *__restrict_
                 }
             }
     }
-    if (VEC && G.S <= 1 && G.fin != FIN_MEAN_M2) {
+    if (VEC && G.S <= 1 && G.fin != FIN_MEAN_M2 && KIND != K_SUMSQ) {
         // unsplit: one 128-bit store per column-vector (with few rows the output is as large as the input, and W scalar
         // stores per thread, 16 bytes apart across the warp, quarter-fill every sector they touch)
 #pragma unroll

@@ -183,7 +183,12 @@ int reduce_typed(feo_ctx *ctx, int kind, T *out, const T *in, const T *aux, int 
                     if (rc1 != -1) return rc1;
                 }
             }
-            T *mean = nullptr;
+            if (partial) return run_plan<T, K_SUMSQ>(ctx, p, out, in, nullptr, FIN_MEAN_M2, n);  // out = S1 x nout | S2 x nout
+            if (ctx->knobs[FEO_KNOB_REDUCE_FUSE] != 3) {
+                // one pass for every other geometry: wrapping sum and sum of squares (see Acc<T, K_SUMSQ>)
+                return run_plan<T, K_SUMSQ>(ctx, p, out, in, nullptr, FIN_DIV, n);
+            }
+            T *mean = nullptr;  // the literal two passes (knob REDUCE_FUSE = 3; kept as the cross-check of the identity)
             FEO_CUDA(ctx, feo_alloc_async(ctx, (void **)&mean, (size_t)p.nout * sizeof(T)));
             int rc = run_plan<T, K_SUM>(ctx, p, mean, in, nullptr, FIN_DIV, n);
             if (rc == FEO_OK) rc = run_plan<T, K_SQDEV>(ctx, p, out, in, mean, FIN_DIV, n);

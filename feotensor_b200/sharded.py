@@ -15,7 +15,8 @@ A ShardedTensor is one dense row-major block of leading rows per rank.  Which op
 
 With a `PeerComm` attached to the engine (`CudaEngine(comm=PeerComm(...))`) the exchange steps above do not call
 NCCL: the local reduction writes its partial straight into a peer-mapped window and ONE kernel per rank signals, waits
-and combines the partials over NVLink in rank order with the epilogue (mean's division, var's Chan merge) fused in
+and combines the partials over NVLink in rank order with the epilogue (mean's division, var's Chan merge -- or, for
+integers, the exact resolution of wrapping sum / sum-of-squares partials) fused in
 (`csrc/peer.cu`).  torch.distributed then only carries the 64-byte IPC handles at start-up.
 
 The local arithmetic goes through an *engine*: `CudaEngine` (the C ABI; the only engine this package ships) --
@@ -371,7 +372,7 @@ class ShardedTensor:
         is_float = dtype.kind == "f"
         comm = getattr(eng, "comm", None)
         if comm is not None and kind in ("sum", "mean", "var", "max", "min") and \
-                nout * dtype.itemsize * (2 if kind == "var" and is_float else 1) <= comm.slot_bytes:
+                nout * dtype.itemsize * (2 if kind == "var" else 1) <= comm.slot_bytes:
             return eng.reshape(eng.reduce_sharded(kind, self.local, local_axes, nout, n_div), out_dims)
 
         def allreduce(t, op):

@@ -150,11 +150,15 @@ FEO_API int feo_reduce(feo_ctx *ctx, int kind, int dtype, void *out, const void 
                int naxes, const size_t *axes);
 /* Building blocks for a tensor sharded on its leading axis:
  *  SUM/MEAN -> per-shard sums, MAX/MIN -> per-shard extrema (combine with an all-reduce);
- *  VAR (floats) -> out holds nout means followed by nout M2 values (combine with feo_var_merge). */
+ *  VAR -> out holds 2 * nout values (combine with feo_var_merge): floats nout means | nout M2;
+ *         integers nout wrapping sums | nout wrapping sums of squares (exact: see feo_var_merge). */
 FEO_API int feo_reduce_partial(feo_ctx *ctx, int kind, int dtype, void *out, const void *in, int rank,
                        const size_t *shape, int naxes, const size_t *axes);
-/* Chan merge of `nparts` equal-count partials laid out [part][mean x nout | M2 x nout], then the
- * division by *divisor_host (one element of dtype): out[o] = M2_total[o] / n. */
+/* Merges `nparts` VAR partials laid out [part][2 x nout], then divides by *divisor_host (one element
+ * of dtype).  Floats: Chan merge of equal-count (mean | M2) partials, out[o] = M2_total[o] / n.
+ * Integers: S1 = sum of the wrapping sums, S2 = sum of the wrapping sums of squares; with
+ * m = S1 / n (truncating) the reference's two-pass result (tensor.rs:171-202) is exactly
+ * (S2 - 2 m S1 + n m^2) / n in wrapping arithmetic (a ring identity modulo 2^k). */
 FEO_API int feo_var_merge(feo_ctx *ctx, int dtype, void *out, const void *partials, size_t nparts, size_t nout,
                   size_t count_per_part, const void *divisor_host);
 /* Second pass of the integer variance (tensor.rs:196-198): out[o] = sum over the removed axes of
@@ -209,7 +213,7 @@ FEO_API int feo_comm_allreduce(feo_comm *comm, int kind, int dtype, void *out, s
 /* Tensor::{sum,mean,var,max,min} (tensor.rs:70-307) of a tensor sharded on its leading axis with
  * axis 0 among the removed axes: `shape` is the LOCAL block, *divisor_host the counted-in-T divisor
  * of the GLOBAL shape (feo_reduce_divisor).  Local one-pass reduction written straight into the
- * window, then the exchange kernel; integer var runs the reference's two passes (two exchanges). */
+ * window, then the exchange kernel (var: one pass and one exchange for floats and integers alike). */
 FEO_API int feo_reduce_sharded(feo_comm *comm, int kind, int dtype, void *out, const void *in, int rank, const size_t *shape,
                        int naxes, const size_t *axes, const void *divisor_host);
 /* All-gather by pulling over NVLink: out = part 0 | part 1 | ...; parts[r] is rank r's buffer (feo_peer_alloc'ed

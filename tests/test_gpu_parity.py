@@ -448,6 +448,34 @@ def test_outputs_stay_inside_their_buffers(feo, oracle):
             np.testing.assert_array_equal(check(buf, want.size, want, f"bcast {dt} {sa} {sb}"), want.reshape(-1))
 
 
+def test_integer_variance_one_pass_equals_the_two_passes(feo, oracle):
+    """Integer var runs as one pass (wrapping sum and sum of squares; the ring identity sum (x - m)^2 = S2 - 2 m S1 + n m^2
+    holds modulo 2^k whatever overflows).  It must give the reference's two-pass result bit for bit -- also when nearly
+    every intermediate wraps -- and agree with the literal two-pass kernels (knob REDUCE_FUSE = 3)."""
+    import feotensor_b200._lib as L
+    ctx = feo.Context.default()
+    rng = np.random.default_rng(303)
+    shapes = [((300, 200, 8), [0]), ((300, 200, 8), [1]), ((300, 200, 8), [0, 2]), ((5000, 3), [0]), ((5000, 3), [1]), ((64, 4099), [1]),
+              ((3, 4, 5, 6, 7), [0, 2, 4]), ((100003,), [0]), ((40, 300, 16), [1]), ((2, 5000), [0])]
+    ranges = {"i32": (-2 ** 31, 2 ** 31 - 1), "u32": (0, 2 ** 32 - 1), "i64": (-2 ** 63, 2 ** 63 - 1)}
+    try:
+        for dt, (lo, hi) in ranges.items():
+            for shape, axes in shapes:
+                for wide in (False, True):
+                    x = rng.integers(lo, hi, shape, dtype=oracle.NP_DTYPES[dt], endpoint=True) if wide else rand(oracle, rng, dt, shape)
+                    t = feo.Tensor(feo.Shape(shape), x)
+                    want = oracle.reduce("var", x, axes)
+                    ctx.tune(L.KNOB_REDUCE_FUSE, 0)
+                    one = t.var(axes).to_numpy()
+                    ctx.tune(L.KNOB_REDUCE_FUSE, 3)
+                    two = t.var(axes).to_numpy()
+                    np.testing.assert_array_equal(one, want, err_msg=f"one-pass {dt} {shape} {axes} wide={wide}")
+                    np.testing.assert_array_equal(two, want, err_msg=f"two-pass {dt} {shape} {axes} wide={wide}")
+    finally:
+        ctx.tune(L.KNOB_REDUCE_FUSE, 0)
+    ctx.arith_flag(clear=True)
+
+
 def test_many_group_reductions_multipass_and_generic_agree(feo, oracle):
     """More than four alternating kept / reduced groups: the multi-pass route (sum / mean / max / min) and the
     one-kernel generic fallback (knob REDUCE_SPLIT = -1; always used for var) give the oracle's integers bit for bit."""
@@ -526,6 +554,22 @@ def test_partial_reductions_and_var_merge(feo, oracle):
                                        2, L.sizes([rows, K]), 1, L.sizes([0])))
         sq = p if sq is None else sq + p
     np.testing.assert_array_equal((sq / n).to_numpy(), oracle.reduce("var", xi, [0]))
+    # ... and in one pass: VAR partials of integers are wrapping (S1 | S2) pairs, merged exactly by feo_var_merge
+    for dt, code in (("i32", L.I32), ("i64", L.I64), ("u32", L.U32)):
+        info = np.iinfo(oracle.NP_DTYPES[dt])
+        xw = rng.integers(info.min, info.max, (G * rows, K), dtype=oracle.NP_DTYPES[dt], endpoint=True)  # nearly everything wraps
+        es = xw.itemsize
+        parts = feo.Tensor.zeros(feo.shape(G, 2, K), dt)
+        for g in range(G):
+            sh = feo.Tensor(feo.shape(rows, K), xw[g * rows:(g + 1) * rows])
+            ctx.check(lib.feo_reduce_partial(ctx.handle, L.VAR, code, C.c_void_p(parts.data.ptr + g * 2 * K * es), C.c_void_p(sh.data.ptr),
+                                             2, L.sizes([rows, K]), 1, L.sizes([0])))
+        outi = feo.Tensor.zeros(feo.shape(K), dt)
+        divi = np.array([oracle.reduce_divisor(dt, (G * rows, K), [0])], oracle.NP_DTYPES[dt])
+        ctx.check(lib.feo_var_merge(ctx.handle, code, C.c_void_p(outi.data.ptr), C.c_void_p(parts.data.ptr), G, K, rows,
+                                    divi.ctypes.data_as(C.c_void_p)))
+        np.testing.assert_array_equal(outi.to_numpy(), oracle.reduce("var", xw, [0]), err_msg=dt)
+    ctx.arith_flag(clear=True)
 
 
 # ---- products ---------------------------------------------------------------------------------------------------------
