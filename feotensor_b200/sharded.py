@@ -9,7 +9,8 @@ A ShardedTensor is one dense row-major block of leading rows per rank.  Which op
       sum / mean      all-reduce(SUM); mean divides by the GLOBAL counted-in-T divisor afterwards
       max / min       all-reduce(MAX / MIN)
       var (floats)    all-gather of per-shard (mean | M2), Chan merge in rank order (deterministic)
-      var (ints)      all-reduce(SUM) -> truncated mean -> squared deviations per shard -> all-reduce -> divide
+      var (ints)      all-gather of per-shard wrapping (sum | sum of squares); m = S1 / n, var = (S2 - 2 m S1 + n m^2) / n
+                      in wrapping arithmetic = the reference's two integer passes, exactly
   dot                                                 all-reduce(SUM) of per-shard partial dots
   matmul (A row-sharded)                              none if B is replicated, else all-gather of B
 
@@ -197,18 +198,11 @@ class CudaEngine:
         return x._reduce(kind, axes)
 
     def reduce_partial(self, kind, x, axes, nout):
-        """SUM/MEAN -> sums, MAX/MIN -> extrema ([nout]); VAR (floats) -> [2, nout] = means | M2."""
+        """SUM/MEAN -> sums, MAX/MIN -> extrema ([nout]); VAR -> [2, nout]: floats means | M2, integers wrapping S1 | S2."""
         ctx, dims = self.ctx, self.dims(x)
         out = self.empty([2, nout] if kind == "var" else [nout], x.dtype)
         ctx.check(ctx.lib.feo_reduce_partial(ctx.handle, L.KIND_CODES[kind], x.data.code, C.c_void_p(out.data.ptr),
                                              C.c_void_p(x.data.ptr), len(dims), L.sizes(dims), len(axes), L.sizes(axes)))
-        return out
-
-    def reduce_sqdev(self, x, mean, axes, nout):
-        ctx, dims = self.ctx, self.dims(x)
-        out = self.empty([nout], x.dtype)
-        ctx.check(ctx.lib.feo_reduce_sqdev(ctx.handle, x.data.code, C.c_void_p(out.data.ptr), C.c_void_p(x.data.ptr),
-                                           C.c_void_p(mean.data.ptr), len(dims), L.sizes(dims), len(axes), L.sizes(axes)))
         return out
 
     def var_merge(self, partials, nparts, nout, count_per_part, divisor):
@@ -369,7 +363,6 @@ class ShardedTensor:
         if axes and 0 not in axes:
             out_local = eng.reduce(kind, self.local, axes)
             return self._like(out_local, out_dims)
-        is_float = dtype.kind == "f"
         comm = getattr(eng, "comm", None)
         if comm is not None and kind in ("sum", "mean", "var", "max", "min") and \
                 nout * dtype.itemsize * (2 if kind == "var" else 1) <= comm.slot_bytes:
@@ -390,22 +383,16 @@ class ShardedTensor:
             return eng.reshape(part, out_dims)
         if kind != "var":
             raise ValueError(f"unknown reduction {kind}")
+        # var: one pass per shard, one exchange.  Floats: (mean | M2) partials, Chan merge in rank order; integers: wrapping
+        # (sum | sum of squares) partials, resolved exactly by feo_var_merge (the reference's two passes are ring arithmetic).
         local_count = int(np.prod([eng.dims(self.local)[a] for a in local_axes]))
-        if is_float:
-            part = eng.reduce_partial("var", self.local, local_axes, nout)  # [2, nout]
-            gathered = part
-            if self.world > 1:
-                gathered = eng.empty([self.world, 2, nout], dtype)
-                dist.all_gather(list(eng.as_torch(gathered).view(self.world, -1).unbind(0)), eng.as_torch(part), group=self.group)
-            merged = eng.var_merge(gathered, self.world, nout, local_count, n_div)
-            return eng.reshape(merged, out_dims)
-        # integers: the reference's own two-pass scheme, exactly (tensor.rs:171-177, 188, 196-202)
-        total = eng.reduce_partial("sum", self.local, local_axes, nout)
-        allreduce(eng.as_torch(total), "sum")
-        mean = eng.scalar("div", total, n_div)
-        sq = eng.reduce_sqdev(self.local, mean, local_axes, nout)
-        allreduce(eng.as_torch(sq), "sum")
-        return eng.reshape(eng.scalar("div", sq, n_div), out_dims)
+        part = eng.reduce_partial("var", self.local, local_axes, nout)  # [2, nout]
+        gathered = part
+        if self.world > 1:
+            gathered = eng.empty([self.world, 2, nout], dtype)
+            dist.all_gather(list(eng.as_torch(gathered).view(self.world, -1).unbind(0)), eng.as_torch(part), group=self.group)
+        merged = eng.var_merge(gathered, self.world, nout, local_count, n_div)
+        return eng.reshape(merged, out_dims)
 
     def dot(self, rhs):
         """Vector::vecmul (vector.rs:71-78) on two identically sharded vectors: a replicated [1] result."""

@@ -58,19 +58,35 @@ class OracleEngine:
     def reduce_partial(self, kind, x, axes, nout):
         if kind == "var":
             ax = tuple(axes)
+            if x.dtype.kind != "f":  # integers: wrapping sum | wrapping sum of squares
+                with np.errstate(over="ignore"):
+                    return np.stack([x.sum(axis=ax, dtype=x.dtype).reshape(-1), (x * x).sum(axis=ax, dtype=x.dtype).reshape(-1)])
             mean = x.astype(np.float64).mean(axis=ax).reshape(-1)
             m2 = ((x.astype(np.float64) - x.astype(np.float64).mean(axis=ax, keepdims=True)) ** 2).sum(axis=ax).reshape(-1)
             return np.stack([mean, m2]).astype(x.dtype)
         return self.o.reduce("sum" if kind == "mean" else kind, x, axes).reshape(-1).copy()
 
-    def reduce_sqdev(self, x, mean, axes, nout):
-        keep = [d for d in range(x.ndim) if d not in axes]
-        m = mean.reshape([x.shape[d] if d in keep else 1 for d in range(x.ndim)])
-        with np.errstate(over="ignore"):
-            c = x - m
-            return (c * c).sum(axis=tuple(axes), dtype=x.dtype).reshape(-1)
-
     def var_merge(self, partials, nparts, nout, count, divisor):
+        if partials.dtype.kind != "f":
+            # exact in the ring Z / 2^k: m = S1 / n (truncating), var = (S2 - 2 m S1 + n m^2) / n; python ints, then wrap
+            bits, signed = partials.dtype.itemsize * 8, partials.dtype.kind == "i"
+
+            def wrap(v):
+                v &= (1 << bits) - 1
+                return v - (1 << bits) if signed and v >= 1 << (bits - 1) else v
+
+            def tdiv(a, b):
+                q = abs(a) // abs(b)
+                return q if (a >= 0) == (b >= 0) else -q
+            p = partials.reshape(nparts, 2, nout)
+            n = int(divisor)
+            out = np.empty(nout, partials.dtype)
+            for o in range(nout):
+                s1 = wrap(sum(int(v) for v in p[:, 0, o]))
+                s2 = wrap(sum(int(v) for v in p[:, 1, o]))
+                m = tdiv(s1, n)
+                out[o] = wrap(tdiv(wrap(s2 - 2 * m * s1 + n * m * m), n))
+            return out
         p = partials.reshape(nparts, 2, nout).astype(np.float64)
         n, mean, m2 = 0.0, np.zeros(nout), np.zeros(nout)
         for g in range(nparts):  # Chan merge in rank order
