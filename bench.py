@@ -518,6 +518,8 @@ def main():
     ring = [torch.empty(slab_elems, dtype=torch.float32).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream()
     main_stream = torch.cuda.current_stream()
+    ctx_copy = feo.Context(local)  # second context on the copy stream: the D2H leg goes through the C ABI too
+    ctx_copy.set_stream(copy_stream.cuda_stream)
 
     def e2e_step():
         ctx.check(lib.feo_upload(h, vp(a.data_ptr()), vp(a_host.data_ptr()), a_host.numel() * 4))
@@ -528,8 +530,8 @@ def main():
             ev = torch.cuda.Event()
             ev.record(main_stream)
             copy_stream.wait_event(ev)
-            with torch.cuda.stream(copy_stream):
-                ring[s % 2].copy_(out[s * slab_elems:(s + 1) * slab_elems], non_blocking=True)
+            ctx_copy.check(lib.feo_download_async(ctx_copy.handle, vp(ring[s % 2].data_ptr()), vp(out.data_ptr() + 4 * s * slab_elems),
+                                                  4 * slab_elems))
         main_stream.wait_stream(copy_stream)
 
     e2e_step()
@@ -549,6 +551,8 @@ def main():
         e2e_ms = float(t.item())
     e2e_val = world * step_bytes_rank * e2e_steps / (e2e_ms * 1e-3) / 1e9
     assert float(ring[(nslabs - 1) % 2][slab_elems - 1].item()) == float(out[nslabs * slab_elems - 1].item())
+    ctx_copy.sync()
+    ctx_copy.close()
     del ring, a_host, b_host
 
     # ---- ncu-derived DRAM traffic of the dominant kernel (profiles/, per launch) if a capture was summarised ----
