@@ -17,6 +17,7 @@
 #pragma once
 
 #include <algorithm>
+#include <array>
 #include <cstddef>
 #include <cstdint>
 #include <memory>
@@ -434,5 +435,98 @@ template <class T> Vector<T> Vector<T>::matmul(const Matrix<T> &rhs) const {
 FEO_WRAPPER_OPS(Vector, +, FEO_ADD) FEO_WRAPPER_OPS(Vector, -, FEO_SUB) FEO_WRAPPER_OPS(Vector, *, FEO_MUL) FEO_WRAPPER_OPS(Vector, /, FEO_DIV)
 FEO_WRAPPER_OPS(Matrix, +, FEO_ADD) FEO_WRAPPER_OPS(Matrix, -, FEO_SUB) FEO_WRAPPER_OPS(Matrix, *, FEO_MUL) FEO_WRAPPER_OPS(Matrix, /, FEO_DIV)
 #undef FEO_WRAPPER_OPS
+
+// ---- cross-GPU epilogues over peer memory (feotensor_b200.h, "cross-GPU epilogues"; one process per GPU) ---------------------
+// The host program carries the 64-byte handles between the ranks with whatever rendezvous it has (MPI, a file, a socket).
+using PeerHandle = std::array<unsigned char, FEO_PEER_HANDLE_BYTES>;
+
+class PeerWindow {  // peer-mappable device memory owned by this rank
+public:
+    PeerWindow(std::shared_ptr<Context> ctx, size_t bytes) : ctx_(std::move(ctx)), bytes_(bytes) { ctx_->check(feo_peer_alloc(ctx_->raw(), bytes, &ptr_)); }
+    ~PeerWindow() { if (ptr_) feo_peer_free(ctx_->raw(), ptr_); }
+    PeerWindow(const PeerWindow &) = delete;
+    PeerWindow &operator=(const PeerWindow &) = delete;
+    PeerHandle export_handle() const {
+        PeerHandle h{};
+        ctx_->check(feo_peer_export(ctx_->raw(), ptr_, h.data()));
+        return h;
+    }
+    void *ptr() const { return ptr_; }
+    size_t bytes() const { return bytes_; }
+
+private:
+    std::shared_ptr<Context> ctx_;
+    void *ptr_ = nullptr;
+    size_t bytes_;
+};
+
+class PeerComm {  // the `world` windows of one node as seen from this rank; every rank issues the same sequence of calls
+public:
+    // handles[r] = rank r's PeerWindow::export_handle(); `own` is this rank's window.  The caller synchronises the ranks
+    // (all windows created and mapped) before the first collective call.
+    PeerComm(std::shared_ptr<Context> ctx, int rank, std::shared_ptr<PeerWindow> own, const std::vector<PeerHandle> &handles)
+        : ctx_(std::move(ctx)), own_(std::move(own)), rank_(rank), world_((int)handles.size()) {
+        std::vector<void *> windows(handles.size());
+        for (size_t r = 0; r < handles.size(); ++r) {
+            if ((int)r == rank) { windows[r] = own_->ptr(); continue; }
+            ctx_->check(feo_peer_open(ctx_->raw(), handles[r].data(), &windows[r]));
+            opened_.push_back(windows[r]);
+        }
+        ctx_->check(feo_comm_create(ctx_->raw(), rank, world_, windows.data(), own_->bytes(), &raw_));
+    }
+    ~PeerComm() {
+        feo_sync(ctx_->raw());
+        feo_comm_destroy(raw_);
+        for (void *p : opened_) feo_peer_close(ctx_->raw(), p);
+    }
+    PeerComm(const PeerComm &) = delete;
+    PeerComm &operator=(const PeerComm &) = delete;
+    int rank() const { return rank_; }
+    int world() const { return world_; }
+    void barrier() const { ctx_->check(feo_comm_barrier(raw_)); }
+
+    // Tensor::{sum,mean,var,max,min} (tensor.rs:70-307) of the GLOBAL tensor whose block of leading rows is `local`; `axes`
+    // contains 0 or is empty (otherwise no exchange is needed: call the local method).  Replicated, bit-identical result.
+    template <class T> Tensor<T> reduce(int kind, const Tensor<T> &local, const Shape &global, const Axes &axes) const {
+        int out_rank = 0;
+        std::vector<size_t> od(global.order() ? global.order() : 1);
+        if (feo_reduce_shape((int)global.order(), global.dims().data(), (int)axes.size(), axes.data(), &out_rank, od.data()) != FEO_OK)
+            throw Panic("axes must be strictly ascending, unique and < order (the reference panics)");
+        od.resize((size_t)out_rank);
+        T divisor{};  // the reference counts it in T over the GLOBAL shape (tensor.rs:112-130)
+        feo_reduce_divisor(Tensor<T>::DT, (int)global.order(), global.dims().data(), (int)axes.size(), axes.data(), &divisor);
+        Axes local_axes = axes;
+        if (local_axes.empty())
+            for (size_t d = 0; d < local.shape().order(); ++d) local_axes.push_back(d);  // axes == [] reduces everything (tensor.rs:84)
+        Shape os(od);
+        Tensor<T> out(os, DeviceStorage<T>(local.data().ctx(), os.size()));
+        ctx_->check(feo_reduce_sharded(raw_, kind, Tensor<T>::DT, out.ptr(), local.ptr(), (int)local.shape().order(), local.shape().dims().data(),
+                                       (int)local_axes.size(), local_axes.data(), &divisor));
+        return out;
+    }
+    // DynamicVector::vecmul (vector.rs:71-78) on two identically sharded vectors: a replicated one-element result.
+    template <class T> Tensor<T> dot(const Tensor<T> &a, const Tensor<T> &b) const {
+        if (a.shape() != b.shape()) throw Panic("assertion failed: self.shape() == rhs.shape()");
+        Tensor<T> out(Shape({1}), DeviceStorage<T>(a.data().ctx(), 1));
+        ctx_->check(feo_dot_sharded(raw_, Tensor<T>::DT, out.ptr(), a.ptr(), b.ptr(), 1, a.size()));
+        return out;
+    }
+    // DynamicMatrix::matmul (matrix.rs:76-90), A row-sharded (a_local = this rank's [M, K] rows) and B row-sharded:
+    // b_panels[r] = rank r's [K / world, N] panel in peer-mapped memory; returns this rank's [M, N] rows.
+    template <class T> Tensor<T> matmul_sharded_b(const Tensor<T> &a_local, const std::vector<const void *> &b_panels, size_t K, size_t N) const {
+        const size_t M = a_local.shape()[0];
+        if (a_local.shape()[1] != K) throw Panic("assertion `left == right` failed");
+        Tensor<T> out(Shape({M, N}), DeviceStorage<T>(a_local.data().ctx(), M * N));
+        ctx_->check(feo_matmul_sharded_b(raw_, FEO_MATMUL_AUTO, Tensor<T>::DT, out.ptr(), a_local.ptr(), b_panels.data(), M, K, N));
+        return out;
+    }
+
+private:
+    std::shared_ptr<Context> ctx_;
+    std::shared_ptr<PeerWindow> own_;
+    feo_comm *raw_ = nullptr;
+    std::vector<void *> opened_;
+    int rank_, world_;
+};
 
 }  // namespace feo

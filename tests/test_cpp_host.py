@@ -33,6 +33,35 @@ def test_cpp_port_compiles_and_links():
     assert os.access(exe, os.X_OK)
 
 
+def test_cpp_peer_communicator_api_compiles(tmp_path):
+    """The multi-GPU wrapper of the C++ host API (PeerWindow / PeerComm) instantiates against the C ABI for every dtype."""
+    src = tmp_path / "peer_api.cpp"
+    src.write_text("""
+#include "feotensor.hpp"
+template <class T> void use(feo::PeerComm &c, const feo::Tensor<T> &x, const feo::Shape &g) {
+    (void)c.reduce(FEO_VAR, x, g, feo::Axes{0});
+    (void)c.dot(x, x);
+    (void)c.matmul_sharded_b(x, std::vector<const void *>{nullptr}, 4, 4);
+}
+int main(int argc, char **) {
+    if (argc > 1000) {  // never runs: this program only has to compile and link
+        auto ctx = std::make_shared<feo::Context>(0);
+        auto win = std::make_shared<feo::PeerWindow>(ctx, 1 << 20);
+        feo::PeerComm comm(ctx, 0, win, {win->export_handle()});
+        comm.barrier();
+        feo::Shape g({4, 4});
+        use(comm, feo::Tensor<float>::zeros(g), g); use(comm, feo::Tensor<double>::zeros(g), g);
+        use(comm, feo::Tensor<int32_t>::zeros(g), g); use(comm, feo::Tensor<int64_t>::zeros(g), g); use(comm, feo::Tensor<uint32_t>::zeros(g), g);
+    }
+    return 0;
+}
+""")
+    exe = tmp_path / "peer_api"
+    subprocess.run(["g++", "-std=c++17", "-O0", "-Wall", "-I" + os.path.join(ROOT, "include"), str(src), "-L" + LIBDIR, "-lfeotensor_b200",
+                    "-Wl,-rpath," + LIBDIR, "-o", str(exe)], check=True)
+    assert os.access(exe, os.X_OK)
+
+
 @pytest.mark.gpu
 def test_cpp_port_of_reference_tests_passes_on_gpu():
     exe = _build()
