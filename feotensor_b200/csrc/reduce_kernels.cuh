@@ -1047,7 +1047,8 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         G.c2 = kz;
         G.xblocks = feo_ceil_div((size_t)c.K1, (size_t)kz);  // blocks along k1
         const long long want = 4 * target_blocks;
-        long long S = forced > 0 ? forced : feo_ceil_div((size_t)want, (size_t)G.xblocks);
+        // enough blocks along k1 already: do not split (every split pays the shared-memory tree and a partial again)
+        long long S = forced > 0 ? forced : (G.xblocks >= target_blocks ? 1 : feo_ceil_div((size_t)want, (size_t)G.xblocks));
         const long long min_rows = (long long)G.lanes * (vec ? 16 : 32);  // two full sweeps per thread
         S = clampll(S, 1, c.R1 / min_rows > 0 ? c.R1 / min_rows : 1);
         G.c1 = feo_ceil_div((size_t)c.R1, (size_t)S);
