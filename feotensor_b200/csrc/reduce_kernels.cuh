@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(kThreads, 3) reduce_cols_kernel(T *__restrict_
 // walked concurrently with 8 sweeps in flight; so a warp still reads whole contiguous rows.  The ly partial rows are
 // combined through shared memory in a fixed tree.
 template <typename T, int KIND, int LOADER, bool VEC>
-__global__ void __launch_bounds__(kThreads) reduce_cols2d_kernel(T *__restrict__ out, void *__restrict__ partial,
+__global__ void __launch_bounds__(kThreads, 3) reduce_cols2d_kernel(T *__restrict__ out, void *__restrict__ partial,
                                                                  const T *__restrict__ in, const T *__restrict__ in2,
                                                                  const T *__restrict__ aux, const __grid_constant__ Geom G,
                                                                  T divisor, int *flag) {
@@ -508,13 +508,23 @@ __global__ void __launch_bounds__(kThreads) reduce_cols2d_kernel(T *__restrict__
             for (int k = 0; k < W; ++k) acc[k].push(v.v[k]);
         }
     }
+    // Rows that sit in the same warp (lanes lx apart) meet through shuffles first: for short rows that is most of the tree
+    // (k2 = 16: 3 of 6 levels) without a barrier each.  Needs whole warps per k1 group and power-of-two lx, ly.
+    int rpw = 1;  // rows already merged per warp
+    if ((lx & (lx - 1)) == 0 && lx <= 16 && (ly & (ly - 1)) == 0 && per >= 32) {
+        rpw = 32 / lx;
+        for (int off = 16; off >= lx; off >>= 1) {
+#pragma unroll
+            for (int k = 0; k < W; ++k) { const Acc<T, KIND> o = shfl_down_acc(acc[k], off); acc[k].merge(o); }
+        }
+    }
 #pragma unroll
     for (int k = 0; k < W; ++k) smem[k][threadIdx.x] = acc[k];
     __syncthreads();
     int st = 1;
     while (st * 2 < ly) st *= 2;  // largest power of two below ly (ly >= 2)
-    for (; st >= 1; st >>= 1) {
-        if (active && ty < st && ty + st < ly) {
+    for (; st >= rpw; st >>= 1) {
+        if (active && (ty & (rpw - 1)) == 0 && ty < st && ty + st < ly) {
 #pragma unroll
             for (int k = 0; k < W; ++k) smem[k][threadIdx.x].merge(smem[k][threadIdx.x + st * lx]);
         }
