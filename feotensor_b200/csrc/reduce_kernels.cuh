@@ -947,6 +947,23 @@ __global__ void __launch_bounds__(kThreads) reduce_generic_pairs_kernel(T *__res
     }
 }
 
+// Later passes of a many-group float variance (run_var_multipass): equal-count Welford partials laid out [k1][r1][k2]
+// (means in `mean`, M2 in `m2`) are merged along r1.  The data is an intermediate a fraction of the input's size, so a
+// thread per output with a serial walk is enough; consecutive threads read consecutive k2.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) welford_pairs_cols_kernel(T *__restrict__ out, const T *__restrict__ mean, const T *__restrict__ m2,
+                                                                      long long K1, long long R1, long long K2, T count, T divisor, int fin) {
+    const long long nout = K1 * K2;
+    const long long o = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (o >= nout) return;
+    const long long k1 = o / K2, k2 = o - k1 * K2;
+    Acc<T, K_WELFORD> acc;
+    acc.init((T)0);
+    const long long base = k1 * R1 * K2 + k2;
+    for (long long r = 0; r < R1; ++r) acc.merge_raw(count, __ldg(mean + base + r * K2), __ldg(m2 + base + r * K2));
+    finalize(acc, out, o, nout, fin, divisor, (int *)nullptr);
+}
+
 // ---- stage 2: merge S partial accumulators per output, in a fixed order (deterministic) -------------------------
 // MODE 0: a thread per output (many outputs); 1: a warp per output; 2: a CTA per output (few outputs, thousands of splits:
 // a full reduction of 1 GiB leaves ~4700 partials, which one warp merged in ~100 us).  Warp / CTA: every lane takes a

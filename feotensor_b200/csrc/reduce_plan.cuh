@@ -69,12 +69,25 @@ int run_multipass(feo_ctx *ctx, const Plan &p, T *out, const T *in, int fin, T d
             rc = run_canonical<T, KIND, LD_PLAIN>(ctx, c, out, cur, nullptr, nullptr, fin, divisor);
             break;
         }
-        const int take = red[m - 1] ? 4 : 3;  // [k r k r] or [k r k]; the groups alternate, so the suffix starts with a kept one
+        // Two ways to peel a pass off.  "Outermost first": reduce the first reduced group with everything inside it treated as
+        // one long kept row -- always the streaming cols kernel at full speed, shrinks the data by that group's extent.
+        // "Suffix": reduce the innermost canonical [k r k (r)] with everything in front treated as kept -- shrinks by r1 * r2
+        // but works on inner slabs that may be tiny ([16]^7: 16 x 16 floats).  Take the first unless it shrinks too little.
+        const int take = red[m - 1] ? 4 : 3;
+        const long long shrink_suffix = ext[m - take + 1] * (take == 4 ? ext[m - 1] : 1);
+        const int lead = red[0] ? 0 : 1;  // index of the outermost reduced group
+        const bool outer_first = ext[lead] >= 8 || ext[lead] >= shrink_suffix;
         Canon s{true, 1, 1, 1, 1};
-        for (int i = 0; i <= m - take; ++i) s.K1 *= ext[i];
-        s.R1 = ext[m - take + 1];
-        s.K2 = ext[m - take + 2];
-        if (take == 4) s.R2 = ext[m - 1];
+        if (outer_first) {
+            for (int i = 0; i < lead; ++i) s.K1 *= ext[i];
+            s.R1 = ext[lead];
+            for (int i = lead + 1; i < m; ++i) s.K2 *= ext[i];
+        } else {
+            for (int i = 0; i <= m - take; ++i) s.K1 *= ext[i];
+            s.R1 = ext[m - take + 1];
+            s.K2 = ext[m - take + 2];
+            if (take == 4) s.R2 = ext[m - 1];
+        }
         T *tmp = nullptr;
         if (feo_alloc_async(ctx, (void **)&tmp, (size_t)(s.K1 * s.K2) * sizeof(T)) != cudaSuccess) {
             rc = feo_fail(ctx, FEO_ERR_CUDA, "out of memory for a %lld-element intermediate", s.K1 * s.K2);
@@ -85,8 +98,20 @@ int run_multipass(feo_ctx *ctx, const Plan &p, T *out, const T *in, int fin, T d
         owned = tmp;
         cur = tmp;
         if (rc != FEO_OK) break;
-        ext[m - take] *= s.K2;  // the suffix's leading kept group absorbs k2
-        m = m - take + 1;
+        if (outer_first) {
+            // group `lead` is gone; its kept neighbours (lead - 1, if any, and lead + 1) become one group
+            if (lead == 0) {
+                for (int i = 1; i < m; ++i) { ext[i - 1] = ext[i]; red[i - 1] = red[i]; }
+                m -= 1;
+            } else {
+                ext[lead - 1] *= ext[lead + 1];
+                for (int i = lead + 2; i < m; ++i) { ext[i - 2] = ext[i]; red[i - 2] = red[i]; }
+                m -= 2;
+            }
+        } else {
+            ext[m - take] *= s.K2;  // the suffix's leading kept group absorbs k2
+            m = m - take + 1;
+        }
     }
     if (owned) cudaFreeAsync(owned, ctx->stream);
     return rc;
@@ -136,6 +161,71 @@ int run_var_twostage(feo_ctx *ctx, const Plan &p, T *out, const T *in, int fin, 
     return rc;
 }
 
+// Float variance, any number of groups, one reduced group per pass from the outside in: the first pass is the streaming
+// cols kernel with Welford accumulators (everything inside the outermost reduced group is one long kept row) and leaves
+// equal-count (mean | M2) partials; each further reduced group is merged away by welford_pairs_cols_kernel on data that is
+// already 1 / (first extent) of the input.  Used when the canonical suffix would shrink the data too little for
+// run_var_twostage ([16]^7: 0.55 -> multi-TB/s).
+template <typename T>
+int run_var_multipass(feo_ctx *ctx, const Plan &p, T *out, const T *in, int fin, T divisor) {
+    long long ext[FEO_MAX_RANK];
+    bool red[FEO_MAX_RANK];
+    int m = p.m;
+    for (int i = 0; i < m; ++i) { ext[i] = p.ext[i]; red[i] = p.red[i]; }
+    auto reduced_left = [&]() { int n = 0; for (int i = 0; i < m; ++i) n += red[i] ? 1 : 0; return n; };
+    auto drop_lead = [&](int lead) {  // group `lead` is gone; its kept neighbours become one group
+        if (lead == 0) {
+            for (int i = 1; i < m; ++i) { ext[i - 1] = ext[i]; red[i - 1] = red[i]; }
+            m -= 1;
+        } else if (lead == m - 1) {
+            m -= 1;
+        } else {
+            ext[lead - 1] *= ext[lead + 1];
+            for (int i = lead + 2; i < m; ++i) { ext[i - 2] = ext[i]; red[i - 2] = red[i]; }
+            m -= 2;
+        }
+    };
+    T *cur = nullptr;       // current partials: means | M2, `ncur` each
+    long long ncur = 0;
+    long long count = 1;
+    int rc = FEO_OK;
+    bool first = true;
+    while (rc == FEO_OK) {
+        const int lead = red[0] ? 0 : 1;
+        long long K1 = 1, K2 = 1;
+        for (int i = 0; i < lead; ++i) K1 *= ext[i];
+        const long long R1 = ext[lead];
+        for (int i = lead + 1; i < m; ++i) K2 *= ext[i];
+        const bool last = reduced_left() == 1;
+        const long long n1 = K1 * K2;
+        T *dst = out;
+        if (!last && feo_alloc_async(ctx, (void **)&dst, (size_t)n1 * 2 * sizeof(T)) != cudaSuccess) {
+            rc = feo_fail(ctx, FEO_ERR_CUDA, "out of memory for a %lld-element intermediate", 2 * n1);
+            break;
+        }
+        const int f = last ? fin : FIN_MEAN_M2;
+        if (first) {
+            const Canon s{true, K1, R1, K2, 1};
+            rc = run_canonical<T, K_WELFORD, LD_PLAIN>(ctx, s, dst, in, nullptr, nullptr, f, divisor);
+        } else {
+            const long long blocks = feo_ceil_div((size_t)n1, (size_t)kThreads);
+            welford_pairs_cols_kernel<T><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(dst, cur, cur + ncur, K1, R1, K2, (T)count, divisor, f);
+            ctx->launches++;
+            ctx->window.clear();
+            if (cudaGetLastError() != cudaSuccess) rc = feo_fail(ctx, FEO_ERR_CUDA, "welford_pairs_cols_kernel launch failed");
+        }
+        if (cur) cudaFreeAsync(cur, ctx->stream);
+        cur = last ? nullptr : dst;
+        ncur = n1;
+        count *= R1;
+        first = false;
+        if (last) break;
+        drop_lead(lead);
+    }
+    if (cur) cudaFreeAsync(cur, ctx->stream);
+    return rc;
+}
+
 template <typename T, int KIND>
 int run_plan(feo_ctx *ctx, const Plan &p, T *out, const T *in, const T *aux, int fin, T divisor) {
     const Canon c = canonicalise(p.m, p.ext, p.red);
@@ -145,8 +235,11 @@ int run_plan(feo_ctx *ctx, const Plan &p, T *out, const T *in, const T *aux, int
     }
     if constexpr (KIND == K_WELFORD) {
         if (ctx->knobs[FEO_KNOB_REDUCE_SPLIT] != -1) {
+            // outermost reduced group wide enough: its streaming pass shrinks the data 8x or more and the rest is cheap
+            if (p.ext[p.red[0] ? 0 : 1] >= 8) return run_var_multipass<T>(ctx, p, out, in, fin, divisor);
             const int rc = run_var_twostage<T>(ctx, p, out, in, fin, divisor);
             if (rc != -1) return rc;
+            return run_var_multipass<T>(ctx, p, out, in, fin, divisor);
         }
     }
     GenericGeom G = p.gen;

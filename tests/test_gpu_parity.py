@@ -324,6 +324,8 @@ REDUCE_CASES = [
     ((4097, 33), [0]), ((20000, 4), [0]), ((7, 9), [0]), ((1, 9), [0]), ((9, 1), [0]),             # cols: ragged / tiny
     ((3, 4, 5, 6, 7), [0, 2, 4]), ((3, 4, 5, 6, 7), [1, 3]), ((2, 3, 4, 5, 6, 7), [0, 2, 4]),      # >4 groups: generic
     ((6, 5, 4, 3), [1, 3]), ((6, 5, 4, 3), [0, 2]), ((6, 5, 4, 3), [1, 2]),
+    ((16, 16, 16, 16, 16), [1, 3]), ((16, 16, 16, 16, 16), [0, 2, 4]), ((9, 3, 17, 8, 5, 12), [1, 3, 5]),  # outermost-first multi-pass
+    ((2, 20, 3, 9, 33, 4), [1, 3, 5]), ((12, 2, 3, 40, 7), [0, 2, 4]),                                 # ... and its suffix alternative
     ((5000, 3), [0]), ((5000, 16), [0]), ((40, 300, 16), [1]), ((40, 300, 3), [1]), ((7, 2, 12), [1]),   # cols2d: short k2 rows
     ((9, 5000, 7), [1]), ((3, 100, 500), [1]), ((100, 128 * 4), [0]),                                 # cols2d at its lx limits / cols
     ((2, 5000), [0]), ((3, 4099), [0]), ((5, 8192), [0]), ((3, 3000, 1025), [1]),                     # cols with few rows, scalar columns
