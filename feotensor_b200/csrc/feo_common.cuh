@@ -23,7 +23,8 @@ enum feo_knob {
     FEO_KNOB_BCAST_L2KEEP = 6,  // L2 evict_last policy on broadcast operands: 0 = on, 1 = off
     FEO_KNOB_REDUCE_FUSE = 7,   // split reductions: last-arriving CTA combines the partials in the same launch: 0 = auto (small inputs), 1 = off, 2 = always
     FEO_KNOB_GATHER_OVERLAP = 8,  // sharded-B matmul: pull B's panels on a side stream while the matmul kernel runs: 0 = on, 1 = off
-    FEO_KNOB_COUNT = 9
+    FEO_KNOB_MATMUL_SIMT = 9,   // SIMT matmul, aligned 4-byte types: 0 = auto (cp.async pipeline), 1 = register double buffering, 2..5 = pipeline variants
+    FEO_KNOB_COUNT = 10
 };
 
 // Address ranges of a launch, for the hazard check that lets independent back-to-back kernels overlap their tails.

@@ -2,7 +2,8 @@
 //
 // C[M,N] = A[M,K] * B[K,N], all dense row-major.  128x128 block tile, 8x8 register tile per thread
 // (256 threads), BK-deep shared-memory panels double-buffered through registers, 128-bit global and
-// shared accesses on the aligned fast path and guarded scalar accesses on ragged shapes.
+// shared accesses on the aligned fast path and guarded scalar accesses on ragged shapes; aligned 4-byte types
+// take the cp.async-pipelined kernel further down (f32 with packed FFMA2).
 // Floats accumulate with FMA in k order per thread (reassociation-free along k, but fused: within the
 // stated tolerance of the reference's separate multiply and add); integers wrap, hence bit-exact.
 // Bound: the FP32 pipe (2*M*N*K flop); this is the parity workhorse and the comparison point for
@@ -133,6 +134,164 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 4 ? 2 : 1)) matmul_sim
     }
 }
 
+
+// ---- aligned 4-byte types: cp.async pipeline -------------------------------------------------------------------------
+// The register-double-buffered kernel above leaves the order of "global load, compute, shared store" to the compiler,
+// and SASS shows the loads of the next panels sunk to just in front of their shared-memory stores (fewer live
+// registers), i.e. a full L2 round trip exposed per k-panel -- ncu: long_scoreboard the top stall, FMA pipe 2/3 busy.
+// Here the panels go global -> shared with cp.async (LDGSTS, no registers), STAGES panels deep, one barrier per panel.
+// A keeps its row-major layout in shared memory ([m][k], k contiguous: no transposing stores); a thread reads its 8 rows
+// KV k-values at a time (a warp touches two distinct rows per access: broadcast, conflict-free at any row stride) and
+// B as before.  Per-thread accumulation order along k is unchanged, so results are bit-identical to the kernel above.
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int PBK = 16;            // k-panel depth (elements)
+constexpr int PAS = PBK + 4;       // A panel row stride: 80 bytes, keeps 16-byte alignment
+constexpr int PBS = BN + 4;        // B panel row stride
+template <int STAGES> constexpr int pipe_smem_bytes() { return STAGES * (BM * PAS + PBK * PBS) * 4; }
+
+// f32 only: two FMAs per instruction on 64-bit register pairs (FFMA2, new with sm_100).  Each lane is an IEEE fused
+// multiply-add, so results are bit-identical to fmaf; what changes is the issue rate and the register-file reads per FMA.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void fma2(unsigned long long &acc, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
+template <typename T, int STAGES, int KV, bool F2, int MINB = 2>
+__global__ void __launch_bounds__(kThreads, MINB) matmul_simt_pipe_kernel(T *__restrict__ C, const T *__restrict__ A, const T *__restrict__ B,
+                                                                        long long M, long long K, long long N) {
+    static_assert(sizeof(T) == 4, "4-byte element types");
+    static_assert(!F2 || std::is_same<T, float>::value, "FFMA2 is f32 only");
+    using F = AVec<T, 4>;
+    using KVec = AVec<T, KV>;
+    extern __shared__ __align__(16) unsigned char pipe_smem[];
+    T *As = reinterpret_cast<T *>(pipe_smem);  // [STAGES][BM][PAS]
+    T *Bs = As + STAGES * BM * PAS;            // [STAGES][PBK][PBS]
+
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;
+    const long long m0 = (long long)blockIdx.y * BM, n0 = (long long)blockIdx.x * BN;
+    // two 16-byte chunks of each panel per thread
+    const T *Ag = A + (m0 + tid / 4) * K + (tid % 4) * 4;     // rows tid/4 and 64 + tid/4, k-chunk tid%4
+    const T *Bg = B + (long long)(tid / 32) * N + n0 + (tid % 32) * 4;  // k-rows tid/32 and 8 + tid/32
+    T *a_dst = As + (tid / 4) * PAS + (tid % 4) * 4;
+    T *b_dst = Bs + (tid / 32) * PBS + (tid % 32) * 4;
+    auto issue = [&](long long kt, int stage) {
+        T *ad = a_dst + stage * (BM * PAS), *bd = b_dst + stage * (PBK * PBS);
+        const T *ag = Ag + kt * PBK, *bg = Bg + kt * PBK * N;
+        cp_async16(ad, ag);
+        cp_async16(ad + 64 * PAS, ag + 64 * K);
+        cp_async16(bd, bg);
+        cp_async16(bd + 8 * PBS, bg + 8 * N);
+    };
+
+    T acc[TM][TN];
+    unsigned long long acc2[TM][TN / 2];  // F2: acc2[i][h] = (C[i][2h], C[i][2h+1]) as one 64-bit pair
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            acc[i][j] = (T)0;
+            acc2[i][j / 2] = 0ull;
+        }
+
+    const long long nkt = K / PBK;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nkt) issue(s, s);
+        cp_async_commit();
+    }
+    int stage = 0;
+    for (long long kt = 0; kt < nkt; ++kt) {
+        cp_async_wait<STAGES - 2>();  // panel kt has landed (this thread's chunks) ...
+        __syncthreads();              // ... and everyone's; everyone is also done reading the stage refilled next
+        {
+            const long long nx = kt + STAGES - 1;
+            int ns = stage + STAGES - 1;
+            if (ns >= STAGES) ns -= STAGES;
+            if (nx < nkt) issue(nx, ns);
+            cp_async_commit();
+        }
+        const T *as = As + stage * (BM * PAS) + (ty * 4) * PAS;
+        const T *bs = Bs + stage * (PBK * PBS) + tx * 4;
+#pragma unroll
+        for (int kk = 0; kk < PBK; kk += KV) {
+            KVec a[TM];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const KVec *>(as + ((i < 4 ? i : 60 + i)) * PAS + kk);
+#pragma unroll
+            for (int k = 0; k < KV; ++k) {
+                if constexpr (F2) {
+                    const ulonglong2 p0 = *reinterpret_cast<const ulonglong2 *>(bs + (kk + k) * PBS);
+                    const ulonglong2 p1 = *reinterpret_cast<const ulonglong2 *>(bs + (kk + k) * PBS + 64);
+                    const unsigned long long b2[TN / 2] = {p0.x, p0.y, p1.x, p1.y};
+#pragma unroll
+                    for (int i = 0; i < TM; ++i) {
+                        const unsigned long long a2 = pack2(a[i].v[k], a[i].v[k]);
+#pragma unroll
+                        for (int h = 0; h < TN / 2; ++h) fma2(acc2[i][h], a2, b2[h]);
+                    }
+                    continue;
+                }
+                const F b0 = *reinterpret_cast<const F *>(bs + (kk + k) * PBS);
+                const F b1 = *reinterpret_cast<const F *>(bs + (kk + k) * PBS + 64);
+                T b[TN];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { b[j] = b0.v[j]; b[4 + j] = b1.v[j]; }
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = mac(acc[i][j], a[i].v[k], b[j]);
+            }
+        }
+        if (++stage == STAGES) stage = 0;
+    }
+    cp_async_wait<0>();
+    if constexpr (F2) {
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int h = 0; h < TN / 2; ++h)
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][2 * h]), "=f"(acc[i][2 * h + 1]) : "l"(acc2[i][h]));
+    }
+
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const long long gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long gn = n0 + (h == 0 ? tx * 4 : 64 + tx * 4);
+            F r;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r.v[j] = acc[i][h * 4 + j];
+            *reinterpret_cast<F *>(C + gm * N + gn) = r;
+        }
+    }
+}
+
+template <typename T, int STAGES, int KV, bool F2, int MINB = 2>
+int launch_pipe(feo_ctx *ctx, dim3 grid, T *C, const T *A, const T *B, size_t M, size_t K, size_t N) {
+    static bool attr_set[64] = {false};  // the opt-in is per device (and per instantiation)
+    const int dev = ctx->device & 63;
+    constexpr int smem = pipe_smem_bytes<STAGES>();
+    if (!attr_set[dev]) {
+        FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_simt_pipe_kernel<T, STAGES, KV, F2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set[dev] = true;
+    }
+    matmul_simt_pipe_kernel<T, STAGES, KV, F2, MINB><<<grid, kThreads, smem, ctx->stream>>>(C, A, B, (long long)M, (long long)K, (long long)N);
+    FEO_LAUNCH_CHECK(ctx);
+    return FEO_OK;
+}
+
 template <typename T>
 int matmul_typed(feo_ctx *ctx, T *C, const T *A, const T *B, size_t M, size_t K, size_t N) {
     constexpr int VN = VecN<T>::value;
@@ -141,6 +300,22 @@ int matmul_typed(feo_ctx *ctx, T *C, const T *A, const T *B, size_t M, size_t K,
     if (grid.y > 65535) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "matmul M too large for the SIMT grid");
     const bool fast = (M % BM == 0) && (N % BN == 0) && (K % BK == 0) && feo_aligned16(A) && feo_aligned16(B) && feo_aligned16(C) &&
                       (sizeof(T) == 4 || ((reinterpret_cast<uintptr_t>(C) & 31u) == 0));
+    if constexpr (sizeof(T) == 4) {
+        // knob MATMUL_SIMT: 0 = auto (cp.async pipeline; f32 with FFMA2), 1 = register double buffering,
+        // 2 = pipeline with scalar FMAs, 3..5 = stage / k-vector variants of the auto choice
+        const int v = ctx->knobs[FEO_KNOB_MATMUL_SIMT];
+        constexpr bool kF = std::is_same<T, float>::value;
+        if (fast && v != 1) {
+            switch (v) {
+                case 2: return launch_pipe<T, 4, 4, false>(ctx, grid, C, A, B, M, K, N);
+                case 3: return launch_pipe<T, 3, 4, kF>(ctx, grid, C, A, B, M, K, N);
+                case 4: return launch_pipe<T, 4, 2, kF>(ctx, grid, C, A, B, M, K, N);
+                case 5: return launch_pipe<T, 5, 4, kF>(ctx, grid, C, A, B, M, K, N);
+                case 6: return launch_pipe<T, 4, 4, kF, 1>(ctx, grid, C, A, B, M, K, N);
+                default: return launch_pipe<T, 4, 4, kF>(ctx, grid, C, A, B, M, K, N);
+            }
+        }
+    }
     if (fast) matmul_simt_kernel<T, true><<<grid, kThreads, 0, ctx->stream>>>(C, A, B, (long long)M, (long long)K, (long long)N);
     else matmul_simt_kernel<T, false><<<grid, kThreads, 0, ctx->stream>>>(C, A, B, (long long)M, (long long)K, (long long)N);
     FEO_LAUNCH_CHECK(ctx);

@@ -631,6 +631,29 @@ def test_matmul_simt_vs_oracle(feo, oracle, dt):
             assert_sum_like(got.to_numpy(), want, terms, k + 1, dt, f"matmul {m}x{k}x{n}")
 
 
+def test_matmul_simt_pipeline_variants_agree(feo, oracle):
+    """Aligned 4-byte SIMT matmul: the cp.async pipeline (auto and every stage / k-vector variant) accumulates in the same
+    per-thread k order as the register-double-buffered kernel, so all of them agree bit for bit -- and with the oracle for
+    integers.  Sizes cover fewer k-panels than pipeline stages, a single panel, and many tiles."""
+    import feotensor_b200._lib as L
+    ctx = feo.Context.default()
+    rng = np.random.default_rng(601)
+    try:
+        for dt in ("f32", "i32", "u32"):
+            for m, k, n in ((128, 16, 128), (128, 32, 256), (256, 48, 128), (384, 1024, 256), (1024, 512, 640)):
+                A, B = rand(oracle, rng, dt, (m, k)), rand(oracle, rng, dt, (k, n))
+                ta, tb = feo.Matrix(feo.shape(m, k), A), feo.Matrix(feo.shape(k, n), B)
+                ctx.tune(L.KNOB_MATMUL_SIMT, 1)
+                base = ta.matmul(tb, algo="simt").to_numpy()
+                if dt in INTS:
+                    np.testing.assert_array_equal(base, oracle.matmul(A, B), err_msg=f"{dt} {m}x{k}x{n}")
+                for v in (0, 2, 3, 4, 5):
+                    ctx.tune(L.KNOB_MATMUL_SIMT, v)
+                    np.testing.assert_array_equal(ta.matmul(tb, algo="simt").to_numpy(), base, err_msg=f"{dt} {m}x{k}x{n} variant {v}")
+    finally:
+        ctx.tune(L.KNOB_MATMUL_SIMT, 0)
+
+
 def test_device_generator_matches_host_twin(feo, oracle):
     for dt, lo, hi in (("f32", -1.0, 1.0), ("f32", 1.0, 2.0), ("f64", -1.0, 1.0), ("i32", -1000, 1000), ("i64", -1000, 1000), ("u32", 0, 2000)):
         t = feo.Tensor.uniform(feo.shape(1000, 37), seed=42, lo=lo, hi=hi, dtype=dt, first_index=12345)

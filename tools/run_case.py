@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--slabs", type=int, default=1)
     ap.add_argument("--nofuse", type=int, default=0, help="1 = two-launch combine for split reductions")
     ap.add_argument("--overlap", type=int, default=0, help="FEO_KNOB_GATHER_OVERLAP (2 = overlapped B pre-pass on one GPU)")
+    ap.add_argument("--simt", type=int, default=0, help="FEO_KNOB_MATMUL_SIMT (1 = register double buffering, 2..5 = pipeline variants)")
     ap.add_argument("--l2keep", type=int, default=0, help="1 = disable the evict_last policy on broadcast operands")
     args = ap.parse_args()
 
@@ -60,6 +61,7 @@ def main():
     ctx.tune(L.KNOB_REDUCE_FUSE, args.nofuse)
     ctx.tune(L.KNOB_BCAST_L2KEEP, args.l2keep)
     ctx.tune(L.KNOB_GATHER_OVERLAP, args.overlap)
+    ctx.tune(L.KNOB_MATMUL_SIMT, args.simt)
     lib, h, vp = ctx.lib, ctx.handle, C.c_void_p
     dt = L.code_of(args.dtype)
     es = L.np_dtype(args.dtype).itemsize
@@ -134,7 +136,7 @@ def main():
         A, B, Cm = dev(m * m), dev(m * m), dev(m * m)
         fill(A, m * m, 8); fill(B, m * m, 9)
         timed(lambda: ctx.check(lib.feo_matmul(h, L.ALGO_CODES[args.algo], dt, vp(Cm.data_ptr()), vp(A.data_ptr()), vp(B.data_ptr()), m, m, m)),
-              f"matmul {m}^3 {args.algo} kc={args.kc}", flop=2.0 * m ** 3)
+              f"matmul {m}^3 {args.dtype} {args.algo} kc={args.kc} simt={args.simt}", flop=2.0 * m ** 3)
     elif args.case == "ceilings":
         # library kernels as yardsticks (not product): pure write, pure read, copy
         n = 1 << 28
