@@ -649,7 +649,7 @@ int broadcast_typed(feo_ctx *ctx, T *out, const T *a, const T *b, int rank, cons
     }
     if (knob != 4) {
         int rc = -1;
-        rc = broadcast_vec<T, OP, 16>(ctx, out, a, b, c, knob);
+        if (knob != 7) rc = broadcast_vec<T, OP, 16>(ctx, out, a, b, c, knob);
         if (rc != -1) return rc;
         rc = launch_flat_bcast<T, OP>(ctx, out, a, b, c);
         if (rc != -1) return rc;

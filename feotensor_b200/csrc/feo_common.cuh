@@ -14,7 +14,7 @@
 
 // ---- context ------------------------------------------------------------------------------------
 enum feo_knob {
-    FEO_KNOB_BCAST_TILE = 0,    // 0 = auto, 2 = 4x4 tiles, 3 = 1x1 vector tiles, 4 = scalar fallback, 5 = never hold+stream, 6 = always (see broadcast_vec)
+    FEO_KNOB_BCAST_TILE = 0,    // 0 = auto, 2 = 4x4 tiles, 3 = 1x1 vector tiles, 4 = scalar fallback, 5 = never hold+stream, 6 = always (see broadcast_vec), 7 = flat-index kernel
     FEO_KNOB_REDUCE_SPLIT = 1,  // 0 = auto, > 0 forced number of splits S, -1 = one-kernel generic fallback instead of multi-pass
     FEO_KNOB_REDUCE_BLOCKS_PER_SM = 2,  // target resident blocks per SM used by the split planner (0 = auto)
     FEO_KNOB_MATMUL_TF32_KC = 3,  // k-blocks (of 32) per TMEM accumulation chunk in the 3xTF32 matmul (0 = default 2)

@@ -1060,6 +1060,15 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
     enum { COLS, COLS2D, MICRO, ROWS } which;
     bool vec = false;
     int r2c = 0, cols_j = 1;
+    // Small inputs (config 1: 8 MiB, L2-resident) are latency-bound: a split buys shorter blocks but pays the publish /
+    // combine tail (1.5-6 us against ~3 us of streaming).  When a block's share of the input is small anyway, one
+    // un-split launch is the fastest plan (graph-replayed, `tools/split_sweep.py`: [64,128,256] over [0,2] 5.96 -> 4.28 us,
+    // over [0] 11.4 -> 5.3, over [1] 11.1 -> 5.1).
+    const size_t in_bytes_all = (size_t)c.K1 * c.R1 * c.K2 * c.R2 * sizeof(T);
+    const bool small_input = forced == 0 && in_bytes_all <= (size_t(32) << 20);
+    auto unsplit_ok = [&](long long block_elems, long long limit_bytes) {
+        return small_input && block_elems * (long long)sizeof(T) <= limit_bytes;
+    };
 
     if (c.R2 == 1 && LOADER != LD_MUL && LOADER != LD_MATVEC && c.R1 >= 2 &&
         c.K2 / ((in_aligned && c.K2 % VN == 0) ? VN : 1) <= kThreads / 2) {
@@ -1078,6 +1087,7 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         long long S = forced > 0 ? forced : (G.xblocks >= target_blocks ? 1 : feo_ceil_div((size_t)want, (size_t)G.xblocks));
         const long long min_rows = (long long)G.lanes * (vec ? 16 : 32);  // two full sweeps per thread
         S = clampll(S, 1, c.R1 / min_rows > 0 ? c.R1 / min_rows : 1);
+        if (unsplit_ok(kz * c.R1 * c.K2, 256 << 10)) S = 1;
         G.c1 = feo_ceil_div((size_t)c.R1, (size_t)S);
         G.S = G.S1 = feo_ceil_div((size_t)c.R1, (size_t)G.c1);
     } else if (c.R2 == 1 && LOADER != LD_MUL && LOADER != LD_MATVEC) {
@@ -1090,6 +1100,7 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         const long long base_blocks = G.xblocks * c.K1;
         long long S = forced > 0 ? forced : feo_ceil_div((size_t)target_blocks, (size_t)base_blocks);
         S = clampll(S, 1, c.R1 >= 32 ? c.R1 / 16 : 1);
+        if (unsplit_ok(c.R1 * kThreads * cols_j * W, 256 << 10)) S = 1;
         G.c1 = feo_ceil_div((size_t)c.R1, (size_t)S);
         G.S = G.S1 = feo_ceil_div((size_t)c.R1, (size_t)G.c1);
     } else if (c.R2 <= 32 && LOADER == LD_PLAIN) {
@@ -1104,6 +1115,7 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         const long long base_blocks = G.xblocks * c.K1;
         long long S = forced > 0 ? forced : feo_ceil_div((size_t)target_blocks, (size_t)base_blocks);
         S = clampll(S, 1, c.R1 >= 32 ? c.R1 / 16 : 1);
+        if (unsplit_ok(c.R1 * c.R2 * kThreads * outs, 256 << 10)) S = 1;
         G.c1 = feo_ceil_div((size_t)c.R1, (size_t)S);
         G.S = G.S1 = feo_ceil_div((size_t)c.R1, (size_t)G.c1);
     } else {
@@ -1121,6 +1133,8 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         long long S = forced > 0 ? forced : feo_ceil_div((size_t)want, (size_t)base_blocks);
         const long long min_elems = 4096;  // keep at least 16 KiB (f32) of work per split
         S = clampll(S, 1, per_out / min_elems > 0 ? per_out / min_elems : 1);
+        // (a block per output streams ~21 GB/s: 64 KiB is ~3 us, what the combine tail costs)
+        if (G.lanes == kThreads && 2 * base_blocks >= ctx->sm_count && unsplit_ok(per_out, 64 << 10)) S = 1;
         // split rows first, then columns
         long long S1 = S < c.R1 ? S : c.R1;
         G.c1 = feo_ceil_div((size_t)c.R1, (size_t)S1);
@@ -1163,7 +1177,11 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         // on multi-GiB inputs the second launch is 0.2 % and the two-stage combine is a little faster.  Knob: 2 = always.
         const size_t in_bytes = (size_t)c.K1 * c.R1 * c.K2 * c.R2 * sizeof(T);
         const int fuse = ctx->knobs[FEO_KNOB_REDUCE_FUSE];
-        if (fuse != 1 && (fuse == 2 || in_bytes <= (size_t(256) << 20)) && (size_t)G.nout <= ctx->counters_len) G.counters = ctx->counters;
+        // The kernels that publish per THREAD (cols, cols2d, micro: one fence + atomic per output and split, then a serial
+        // merge by the last arriver) lose to the second launch even on the GPU clock ([64,128,256] over [0]: 11.4 vs 4.9 us,
+        // over [0,1] with 128 splits: 31 vs 6.0), so only the rows kernel (one atomic per block, warp-parallel merge) fuses.
+        const bool fuse_auto = which == ROWS && in_bytes <= (size_t(256) << 20);
+        if (fuse != 1 && (fuse == 2 || fuse_auto) && (size_t)G.nout <= ctx->counters_len) G.counters = ctx->counters;
     }
     int *flag = ctx->arith_flag;
     if (which == COLS) {

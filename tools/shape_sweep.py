@@ -21,6 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--only", default="")
+    ap.add_argument("--match", default="", help="run only the cases whose label contains this text")
     ap.add_argument("--tile", type=int, default=0, help="FEO_KNOB_BCAST_TILE")
     args = ap.parse_args()
     import numpy as np
@@ -77,6 +78,8 @@ def main():
     ]
     if args.only in ("", "reduce"):
         for dt, shape, axes in reduce_cases:
+            if args.match and args.match not in f"reduce {dt} {shape} axes {axes}":
+                continue
             es = L.np_dtype(dt).itemsize
             nin = int(np.prod(shape))
             nout = int(np.prod([e for d, e in enumerate(shape) if d not in axes])) if len(axes) < len(shape) else 1
@@ -102,6 +105,8 @@ def main():
     ]
     if args.only in ("", "bcast"):
         for dt, shape, am, bm in bcast_cases:
+            if args.match and args.match not in f"bcast mul {dt} {shape} a{am} b{bm}":
+                continue
             es = L.np_dtype(dt).itemsize
 
             def strides(mask):
