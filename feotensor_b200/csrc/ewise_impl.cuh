@@ -426,47 +426,93 @@ template <int RANK> __device__ __forceinline__ void flat_decode(unsigned int i, 
     oa += rem * P.sa[0]; ob += rem * P.sb[0];
 }
 
+// U flat indices decoded together: each dim's divisor and strides are fetched once and applied to all U.  ncu on the
+// one-at-a-time version ([16]^7): the parameter fetches (26 LDC.64 per vector, re-issued every loop trip) kept the ADU pipe
+// 94 % busy with mio_throttle / short_scoreboard on top -- the constant bank, not HBM, was the bound (2.5 TB/s).
+template <int RANK, int U> __device__ __forceinline__ void flat_decode_multi(const unsigned int (&i)[U], const FlatParams<RANK> &P,
+                                                                            unsigned int (&oa)[U], unsigned int (&ob)[U], unsigned int (&inner)[U]) {
+    unsigned int rem[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { oa[u] = 0; ob[u] = 0; rem[u] = i[u]; }
+#pragma unroll
+    for (int d = RANK - 1; d >= 1; --d) {
+        const FastDiv f = P.ext[d];
+        const unsigned int sa = P.sa[d], sb = P.sb[d];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned int q = fd_div(rem[u], f);
+            const unsigned int c = rem[u] - q * f.d;
+            if (d == RANK - 1) inner[u] = c;
+            oa[u] += c * sa; ob[u] += c * sb;
+            rem[u] = q;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (RANK == 1) inner[u] = rem[u];
+        oa[u] += rem[u] * P.sa[0]; ob[u] += rem[u] * P.sb[0];
+    }
+}
+
 template <typename T, int OP, int RANK>
 __global__ void __launch_bounds__(kThreads) bcast_flat_kernel(T *__restrict__ out, const T *__restrict__ a, const T *__restrict__ b,
                                                               const __grid_constant__ FlatParams<RANK> P, int *flag) {
     constexpr int VN = VecN<T>::value;
+    constexpr int U = 2;  // vectors per loop trip (4 is slower: 3.0 vs 3.7 TB/s on [16]^7, registers)
     using V = AVec<T, VN>;
     const unsigned int nvec = P.n / VN;
     const unsigned int ext_in = P.ext[RANK - 1].d, sa_in = P.sa[RANK - 1], sb_in = P.sb[RANK - 1];
-    for (unsigned int v = blockIdx.x * kThreads + threadIdx.x; v < nvec; v += gridDim.x * kThreads) {
-        const unsigned int i0 = v * VN;
-        unsigned int oa, ob, inner;
-        flat_decode<RANK>(i0, P, oa, ob, inner);
-        T x[VN], y[VN];
-        if (inner + VN <= ext_in) {  // the whole vector sits in one row
-            if (sa_in == 1 && (reinterpret_cast<uintptr_t>(a + oa) & 15u) == 0) {
-                const V t = *reinterpret_cast<const V *>(a + oa);
+    const unsigned int stride = gridDim.x * kThreads;
+    for (unsigned int v0 = blockIdx.x * kThreads + threadIdx.x; v0 < nvec; v0 += U * stride) {
+        unsigned int i0[U], oa[U], ob[U], inner[U];
 #pragma unroll
-                for (int k = 0; k < VN; ++k) x[k] = t.v[k];
-            } else {
-#pragma unroll
-                for (int k = 0; k < VN; ++k) x[k] = __ldg(a + oa + k * sa_in);
-            }
-            if (sb_in == 1 && (reinterpret_cast<uintptr_t>(b + ob) & 15u) == 0) {
-                const V t = *reinterpret_cast<const V *>(b + ob);
-#pragma unroll
-                for (int k = 0; k < VN; ++k) y[k] = t.v[k];
-            } else {
-#pragma unroll
-                for (int k = 0; k < VN; ++k) y[k] = __ldg(b + ob + k * sb_in);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < VN; ++k) {
-                unsigned int ka = oa + k * sa_in, kb = ob + k * sb_in, dummy;
-                if (inner + k >= ext_in) flat_decode<RANK>(i0 + k, P, ka, kb, dummy);
-                x[k] = __ldg(a + ka); y[k] = __ldg(b + kb);
-            }
+        for (int u = 0; u < U; ++u) {
+            const unsigned int v = v0 + u * stride;
+            i0[u] = (v < nvec ? v : v0) * VN;  // a trip's missing tail vectors redo the first one (not stored)
         }
-        V r;
+        flat_decode_multi<RANK, U>(i0, P, oa, ob, inner);
 #pragma unroll
-        for (int k = 0; k < VN; ++k) r.v[k] = apply_op<OP>(x[k], y[k], flag);
-        st_stream(reinterpret_cast<V *>(out + i0), r);
+        for (int u = 0; u < U; ++u) {
+            if (v0 + u * stride >= nvec) break;
+            T x[VN], y[VN];
+            if (inner[u] + VN <= ext_in) {  // the whole vector sits in one row
+                if (sa_in == 1 && (reinterpret_cast<uintptr_t>(a + oa[u]) & 15u) == 0) {
+                    const V t = *reinterpret_cast<const V *>(a + oa[u]);
+#pragma unroll
+                    for (int k = 0; k < VN; ++k) x[k] = t.v[k];
+                } else if (sa_in == 0) {
+                    const T t = __ldg(a + oa[u]);
+#pragma unroll
+                    for (int k = 0; k < VN; ++k) x[k] = t;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VN; ++k) x[k] = __ldg(a + oa[u] + k * sa_in);
+                }
+                if (sb_in == 1 && (reinterpret_cast<uintptr_t>(b + ob[u]) & 15u) == 0) {
+                    const V t = *reinterpret_cast<const V *>(b + ob[u]);
+#pragma unroll
+                    for (int k = 0; k < VN; ++k) y[k] = t.v[k];
+                } else if (sb_in == 0) {
+                    const T t = __ldg(b + ob[u]);
+#pragma unroll
+                    for (int k = 0; k < VN; ++k) y[k] = t;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VN; ++k) y[k] = __ldg(b + ob[u] + k * sb_in);
+                }
+            } else {  // the vector straddles a row end (always, when the inner extent is below VN): decode its elements together
+                unsigned int ie[VN], ka[VN], kb[VN], dummy[VN];
+#pragma unroll
+                for (int k = 0; k < VN; ++k) ie[k] = i0[u] + k;
+                flat_decode_multi<RANK, VN>(ie, P, ka, kb, dummy);
+#pragma unroll
+                for (int k = 0; k < VN; ++k) { x[k] = __ldg(a + ka[k]); y[k] = __ldg(b + kb[k]); }
+            }
+            V r;
+#pragma unroll
+            for (int k = 0; k < VN; ++k) r.v[k] = apply_op<OP>(x[k], y[k], flag);
+            st_stream(reinterpret_cast<V *>(out + i0[u]), r);
+        }
     }
     // the last n % VN elements
     if (blockIdx.x == 0 && threadIdx.x < P.n - nvec * VN) {
@@ -526,7 +572,7 @@ int launch_flat_bcast(feo_ctx *ctx, T *out, const T *a, const T *b, const Collap
 
 // Vector path with VB-byte accesses; returns -1 when the shape / alignment does not allow it.
 template <typename T, int OP, int VB>
-int broadcast_vec(feo_ctx *ctx, T *out, const T *a, const T *b, const Collapsed &c, int knob) {
+int broadcast_vec(feo_ctx *ctx, T *out, const T *a, const T *b, const Collapsed &c, int knob, bool may_defer = false) {
     constexpr int VN = VecW<T, VB>::value;
     const int in = c.rank - 1;
     auto aligned = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & (uintptr_t)(VB - 1)) == 0; };
@@ -570,6 +616,9 @@ int broadcast_vec(feo_ctx *ctx, T *out, const T *a, const T *b, const Collapsed 
     P.keep_operands = (ctx->knobs[FEO_KNOB_BCAST_L2KEEP] != 1);
 
     const bool both = pd >= 0 && qd >= 0;
+    // Many short alternating axes ([16]^7 with a and b on alternate axes): the P x Q x inner tile is a few KiB and every CTA
+    // decodes the other dims with 64-bit div / mod -- the flat-index kernel is 2.6x faster there (0.96 -> 2.5 TB/s).
+    if (both && may_defer && knob == 0 && P.nrest >= 2 && P.ni_vec * P.np * P.nq < 4096) return -2;
     if (both && knob != 3) {
         // Both operands are invariant somewhere (config 2: a along q, b along p): PT x QT register tile.  Measured on
         // B200 (profiles/): 8x4 un-pipelined tiles beat the pipelined hold+stream form here (6.3 vs 5.8 TB/s per 1 GiB
@@ -649,7 +698,11 @@ int broadcast_typed(feo_ctx *ctx, T *out, const T *a, const T *b, int rank, cons
     }
     if (knob != 4) {
         int rc = -1;
-        if (knob != 7) rc = broadcast_vec<T, OP, 16>(ctx, out, a, b, c, knob);
+        if (knob != 7) rc = broadcast_vec<T, OP, 16>(ctx, out, a, b, c, knob, true);
+        if (rc == -2) {  // the vector planner prefers the flat kernel; fall back to its own tiles if that cannot take the shape
+            rc = launch_flat_bcast<T, OP>(ctx, out, a, b, c);
+            if (rc == -1) rc = broadcast_vec<T, OP, 16>(ctx, out, a, b, c, knob, false);
+        }
         if (rc != -1) return rc;
         rc = launch_flat_bcast<T, OP>(ctx, out, a, b, c);
         if (rc != -1) return rc;

@@ -265,6 +265,8 @@ BCAST_CASES = [
     ((9, 1, 5, 3), (1, 4, 5, 1)),       # rank 4, inner splat
     ((257, 1), (1, 4099)),              # outer product with an odd row length
     ((3, 1, 5, 1, 7, 3), (1, 2, 1, 4, 7, 3)),  # rank 5 after collapsing: generic fallback
+    ((8, 1, 8, 1, 8, 1, 8), (1, 8, 1, 8, 1, 8, 1)),  # alternating short axes: the vector planner defers to the flat-index kernel
+    ((4, 1, 6, 1, 5, 16), (1, 3, 1, 2, 1, 16)),      # ... with a shared inner axis
 ]
 
 
@@ -293,7 +295,7 @@ def test_broadcast_tile_variants_agree(feo, oracle):
     ta, tb = feo.Tensor(feo.shape(19, 1, 256), a), feo.Tensor(feo.shape(1, 23, 256), b)
     want = oracle.ewise_broadcast("mul", a, b)
     try:
-        for knob in (0, 2, 3, 4, 5, 6):
+        for knob in (0, 2, 3, 4, 5, 6, 7):
             for lchunk in (0, 1, 5, 64):
                 ctx.tune(L.KNOB_BCAST_TILE, knob)
                 ctx.tune(L.KNOB_BCAST_LCHUNK, lchunk)
