@@ -208,7 +208,7 @@ def run_suite(torch, feo, L, ctx, hbm_peak, tf_peak):
     def fill(t, n, seed, lo=-1.0, hi=1.0):
         ctx.check(ctx.lib.feo_fill_uniform(ctx.handle, L.F32, vp(t.data_ptr()), n, seed, 0, lo, hi))
 
-    def reduce_case(name, x, shape, axes, kinds, iters):
+    def reduce_case(name, x, shape, axes, kinds, iters, graph_calls=0):
         dims, nout = list(shape), 1
         for d, e in enumerate(shape):
             if d not in axes:
@@ -224,8 +224,21 @@ def run_suite(torch, feo, L, ctx, hbm_peak, tf_peak):
                                                       len(dims), L.sizes(dims), len(axes), L.sizes(axes)))
             ms = timed(torch, fn, iters)
             gbs = 4 * (nin + nout) / ms / 1e6
-            suite[f"{name}_{kind}_axes{''.join(map(str, axes)) or 'all'}"] = {"ms": round(ms, 4), "GB/s": round(gbs, 1),
-                                                                             "frac_hbm": round(gbs / hbm_peak, 3)}
+            key = f"{name}_{kind}_axes{''.join(map(str, axes)) or 'all'}"
+            suite[key] = {"ms": round(ms, 4), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / hbm_peak, 3)}
+            if graph_calls:
+                # launch-bound sizes: the eager figure above is the host's cost per call (ctypes + planning + launch); the GPU's own
+                # time per call is what a captured CUDA graph of back-to-back calls replays at
+                fn()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=torch.cuda.current_stream()):
+                    for _ in range(graph_calls):
+                        fn()
+                us = timed(torch, g.replay, 20, 2) / graph_calls * 1e3
+                suite[key].update({"gpu_us_graph_replay": round(us, 2), "GB/s_graph_replay": round(4 * (nin + nout) / us / 1e3, 1),
+                                   "note": "8 MiB input: L2-resident, latency-bound; eager ms is host-bound"})
+                del g
         del out
 
     # C1: f32 [64,128,256] add / mul + sum/mean/var over [0,2] (8 MiB: L2-resident, launch-bound)
@@ -236,7 +249,7 @@ def run_suite(torch, feo, L, ctx, hbm_peak, tf_peak):
         ms = timed(torch, lambda: ctx.check(ctx.lib.feo_ewise(ctx.handle, L.OP_CODES[op], L.F32, vp(o.data_ptr()), vp(x.data_ptr()),
                                                                vp(y.data_ptr()), n1)), 50, 3)
         suite[f"C1_{op}"] = {"ms": round(ms, 5), "GB/s": round(12 * n1 / ms / 1e6, 1), "note": "8 MiB operands: L2-resident, launch-bound"}
-    reduce_case("C1", x, (64, 128, 256), [0, 2], ("sum", "mean", "var"), 50)
+    reduce_case("C1", x, (64, 128, 256), [0, 2], ("sum", "mean", "var"), 50, graph_calls=20)
     del x, y, o
 
     # C3: f32 [16384,16384,8] (8 GiB) sum / var / max over leading, inner, mixed and all axes

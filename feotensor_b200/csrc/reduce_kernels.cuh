@@ -331,7 +331,7 @@ struct Geom {
 // J column-vectors per thread (kThreads apart): J = 1 with 8 rows in flight is the streaming shape; J = 4 is used when
 // there are fewer than 8 rows in all ([2, n] or [3, n] over axis 0: the loads in flight come from the columns instead).
 template <typename T, int KIND, int LOADER, bool VEC, int J>
-__global__ void __launch_bounds__(kThreads, 3) reduce_cols_kernel(T *__restrict__ out, void *__restrict__ partial,
+__global__ void __launch_bounds__(kThreads, (J > 1 && VEC && KIND == K_WELFORD) ? 2 : 3) reduce_cols_kernel(T *__restrict__ out, void *__restrict__ partial,
                                                                const T *__restrict__ in, const T *__restrict__ in2,
                                                                const T *__restrict__ aux, const __grid_constant__ Geom G,
                                                                T divisor, int *flag) {
@@ -357,7 +357,9 @@ __global__ void __launch_bounds__(kThreads, 3) reduce_cols_kernel(T *__restrict_
         for (int k = 0; k < W; ++k) acc[j][k].init(live[j] ? aux_val<KIND>(aux, o0 + (long long)j * kThreads * W + k) : (T)0);
     }
     long long r = r_lo;
-    for (; r + U <= r_hi; r += U) {
+    // J > 1 is only planned for fewer than 8 rows in all: the U-row loop would never run there, and compiling it in cost the
+    // few-row kernels 0.8-1.3 KB of spills (80-register cap)
+    for (; J == 1 && r + U <= r_hi; r += U) {
         V v[J][U];
 #pragma unroll
         for (int j = 0; j < J; ++j)
