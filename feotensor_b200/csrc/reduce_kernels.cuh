@@ -1098,6 +1098,10 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         const long long W = vec ? VN : 1;
         // few rows: the columns must supply the loads in flight, 4 column-vectors per thread
         cols_j = (c.R1 < 8 && c.K2 / W >= 4 * kThreads) ? 4 : 1;
+        // scalar columns ([3, n] with odd n: rows 1 and 2 start off the 16-byte grid): 4 columns x 3 rows of 4-byte loads are
+        // only 48 bytes in flight per thread -- take 8 columns: sum 3.6 -> 4.7 TB/s (knob REDUCE_BLOCKS_PER_SM = -8 keeps 4 for comparison)
+        // (not for float variance: its three-word accumulators push the 8-column form into spills, 2.4 -> 1.9 TB/s)
+        if (cols_j == 4 && !vec && KIND != K_WELFORD && c.K2 >= 64 * kThreads && ctx->knobs[FEO_KNOB_REDUCE_BLOCKS_PER_SM] != -8) cols_j = 8;
         G.xblocks = feo_ceil_div((size_t)(c.K2 / W), (size_t)kThreads * cols_j);
         const long long base_blocks = G.xblocks * c.K1;
         long long S = forced > 0 ? forced : feo_ceil_div((size_t)target_blocks, (size_t)base_blocks);
@@ -1192,6 +1196,9 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         constexpr int L = (LOADER == LD_VECMAT) ? LD_VECMAT : LD_PLAIN;
         if (vec && cols_j == 1) reduce_cols_kernel<T, KIND, L, true, 1><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
         else if (vec) reduce_cols_kernel<T, KIND, L, true, 4><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
+        else if (cols_j == 8) {
+            if constexpr (KIND != K_WELFORD) reduce_cols_kernel<T, KIND, L, false, 8><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
+        }
         else if (cols_j == 1) reduce_cols_kernel<T, KIND, L, false, 1><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
         else reduce_cols_kernel<T, KIND, L, false, 4><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
     } else if (which == COLS2D) {

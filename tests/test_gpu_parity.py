@@ -226,6 +226,16 @@ def test_elementwise_special_values_and_wrap(feo, oracle):
     r = (ti / feo.Tensor(feo.shape(4), np.array([1, -1, 0, 1], np.int32))).to_numpy()
     assert ctx.arith_flag() == 1 and ctx.arith_flag() == 0
     np.testing.assert_array_equal(r, np.array([2 ** 31 - 1, 0, 0, -7], np.int32))
+    # i64: operands inside the i32 range take a 32-bit division, everything else the 64-bit one -- same quotients either way
+    la = np.array([7, -7, 2 ** 31 - 1, -2 ** 31, -2 ** 31, 2 ** 31, -2 ** 31 - 1, 2 ** 62, -2 ** 63, -2 ** 63, 10 ** 15, -10 ** 15, 5, 0],
+                  np.int64)
+    lb = np.array([2, 2, -1, -1, 1, -1, 3, -3, 1, 2, 7, 10 ** 6, 2 ** 40, -9], np.int64)
+    tl, tm = feo.Tensor(feo.shape(la.size), la), feo.Tensor(feo.shape(lb.size), lb)
+    np.testing.assert_array_equal((tl / tm).to_numpy(), oracle.ewise("div", la, lb))
+    assert ctx.arith_flag() == 0
+    r = (tl / feo.Tensor(feo.shape(la.size), np.array([1, 0, 1, 1, 1, 1, 1, 1, -1, 1, 1, 1, 1, 1], np.int64))).to_numpy()
+    assert ctx.arith_flag() == 1 and ctx.arith_flag() == 0
+    assert r[1] == 0 and r[8] == 0 and r[0] == 7 and r[7] == 2 ** 62
 
 
 def test_elementwise_unaligned_pointers(feo, oracle):
@@ -331,6 +341,7 @@ REDUCE_CASES = [
     ((5000, 3), [0]), ((5000, 16), [0]), ((40, 300, 16), [1]), ((40, 300, 3), [1]), ((7, 2, 12), [1]),   # cols2d: short k2 rows
     ((9, 5000, 7), [1]), ((3, 100, 500), [1]), ((100, 128 * 4), [0]),                                 # cols2d at its lx limits / cols
     ((2, 5000), [0]), ((3, 4099), [0]), ((5, 8192), [0]), ((3, 3000, 1025), [1]),                     # cols with few rows, scalar columns
+    ((3, 16385), [0]), ((7, 40001), [0]), ((2, 3, 17001), [1]),                                       # ... 8 scalar columns per thread
     ((300, 4099), [1]), ((64, 1 << 15), [1]), ((17, 100001), [1]),                                    # rows, unaligned lengths
     ((200, 5, 11), [0, 2]), ((4000, 9), [1]), ((300, 31), [1]), ((300, 17, 3), [2]),                  # micro, run-time r2 incl. > 8
     ((1,), [0]), ((1, 1, 1), [1]), ((2, 1, 3), [1]),

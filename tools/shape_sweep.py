@@ -21,6 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--only", default="")
+    ap.add_argument("--bpsm", type=int, default=0, help="FEO_KNOB_REDUCE_BLOCKS_PER_SM")
     ap.add_argument("--match", default="", help="run only the cases whose label contains this text")
     ap.add_argument("--tile", type=int, default=0, help="FEO_KNOB_BCAST_TILE")
     args = ap.parse_args()
@@ -36,6 +37,7 @@ def main():
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     lib, h, vp = ctx.lib, ctx.handle, C.c_void_p
     ctx.tune(L.KNOB_BCAST_TILE, args.tile)
+    ctx.tune(L.KNOB_REDUCE_BLOCKS_PER_SM, args.bpsm)
 
     def dev(nbytes):
         return torch.empty(nbytes, dtype=torch.uint8, device="cuda")
