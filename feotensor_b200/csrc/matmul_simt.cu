@@ -2,8 +2,8 @@
 //
 // C[M,N] = A[M,K] * B[K,N], all dense row-major.  128x128 block tile, 8x8 register tile per thread
 // (256 threads), BK-deep shared-memory panels double-buffered through registers, 128-bit global and
-// shared accesses on the aligned fast path and guarded scalar accesses on ragged shapes; aligned 4-byte types
-// take the cp.async-pipelined kernel further down (f32 with packed FFMA2).
+// shared accesses on the aligned fast path and guarded scalar accesses on ragged shapes; aligned shapes
+// take the cp.async-pipelined kernel further down (f32 with packed FFMA2); so do aligned 8-byte types.
 // Floats accumulate with FMA in k order per thread (reassociation-free along k, but fused: within the
 // stated tolerance of the reference's separate multiply and add); integers wrap, hence bit-exact.
 // Bound: the FP32 pipe (2*M*N*K flop); this is the parity workhorse and the comparison point for
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 4 ? 2 : 1)) matmul_sim
 }
 
 
-// ---- aligned 4-byte types: cp.async pipeline -------------------------------------------------------------------------
+// ---- aligned shapes: cp.async pipeline -------------------------------------------------------------------------
 // The register-double-buffered kernel above leaves the order of "global load, compute, shared store" to the compiler,
 // and SASS shows the loads of the next panels sunk to just in front of their shared-memory stores (fewer live
 // registers), i.e. a full L2 round trip exposed per k-panel -- ncu: long_scoreboard the top stall, FMA pipe 2/3 busy.
@@ -150,10 +150,17 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int PBK = 16;            // k-panel depth (elements)
-constexpr int PAS = PBK + 4;       // A panel row stride: 80 bytes, keeps 16-byte alignment
-constexpr int PBS = BN + 4;        // B panel row stride
-template <int STAGES> constexpr int pipe_smem_bytes() { return STAGES * (BM * PAS + PBK * PBS) * 4; }
+// Panel geometry in bytes is the same for 4- and 8-byte elements: an A row is 64 bytes (four 16-byte chunks: 16 or 8
+// k-values), rows are padded by one chunk, and both panels are 512 chunks = two per thread.
+template <typename T> struct PipeGeom {
+    static constexpr int VN = 16 / (int)sizeof(T);  // elements per 16-byte chunk
+    static constexpr int PBK = 4 * VN;              // k-panel depth: 16 (4-byte) or 8 (8-byte)
+    static constexpr int PAS = PBK + VN;            // A panel row stride (elements): 80 bytes
+    static constexpr int PBS = BN + VN;             // B panel row stride (elements)
+    static constexpr int CPR = BN / VN;             // chunks per B row: 32 or 64
+    static constexpr int stage_elems = BM * PAS + PBK * PBS;
+};
+template <typename T, int STAGES> constexpr int pipe_smem_bytes() { return STAGES * PipeGeom<T>::stage_elems * (int)sizeof(T); }
 
 // f32 only: two FMAs per instruction on 64-bit register pairs (FFMA2, new with sm_100).  Each lane is an IEEE fused
 // multiply-add, so results are bit-identical to fmaf; what changes is the issue rate and the register-file reads per FMA.
@@ -169,9 +176,12 @@ __device__ __forceinline__ void fma2(unsigned long long &acc, unsigned long long
 template <typename T, int STAGES, int KV, bool F2, int MINB = 2>
 __global__ void __launch_bounds__(kThreads, MINB) matmul_simt_pipe_kernel(T *__restrict__ C, const T *__restrict__ A, const T *__restrict__ B,
                                                                         long long M, long long K, long long N) {
-    static_assert(sizeof(T) == 4, "4-byte element types");
     static_assert(!F2 || std::is_same<T, float>::value, "FFMA2 is f32 only");
+    using PG = PipeGeom<T>;
+    constexpr int VN = PG::VN, PBK = PG::PBK, PAS = PG::PAS, PBS = PG::PBS, CPR = PG::CPR;
+    static_assert(PBK % KV == 0 && KV * sizeof(T) <= 16, "a is read in 16-byte (or narrower) k-vectors");
     using F = AVec<T, 4>;
+    using BV = AVec<T, VN>;  // one 16-byte chunk of a B row
     using KVec = AVec<T, KV>;
     extern __shared__ __align__(16) unsigned char pipe_smem[];
     T *As = reinterpret_cast<T *>(pipe_smem);  // [STAGES][BM][PAS]
@@ -181,17 +191,17 @@ __global__ void __launch_bounds__(kThreads, MINB) matmul_simt_pipe_kernel(T *__r
     const int tx = tid % 16, ty = tid / 16;
     const long long m0 = (long long)blockIdx.y * BM, n0 = (long long)blockIdx.x * BN;
     // two 16-byte chunks of each panel per thread
-    const T *Ag = A + (m0 + tid / 4) * K + (tid % 4) * 4;     // rows tid/4 and 64 + tid/4, k-chunk tid%4
-    const T *Bg = B + (long long)(tid / 32) * N + n0 + (tid % 32) * 4;  // k-rows tid/32 and 8 + tid/32
-    T *a_dst = As + (tid / 4) * PAS + (tid % 4) * 4;
-    T *b_dst = Bs + (tid / 32) * PBS + (tid % 32) * 4;
+    const T *Ag = A + (m0 + tid / 4) * K + (tid % 4) * VN;                  // rows tid/4 and 64 + tid/4, k-chunk tid%4
+    const T *Bg = B + (long long)(tid / CPR) * N + n0 + (tid % CPR) * VN;   // k-rows tid/CPR and PBK/2 + tid/CPR
+    T *a_dst = As + (tid / 4) * PAS + (tid % 4) * VN;
+    T *b_dst = Bs + (tid / CPR) * PBS + (tid % CPR) * VN;
     auto issue = [&](long long kt, int stage) {
         T *ad = a_dst + stage * (BM * PAS), *bd = b_dst + stage * (PBK * PBS);
         const T *ag = Ag + kt * PBK, *bg = Bg + kt * PBK * N;
         cp_async16(ad, ag);
         cp_async16(ad + 64 * PAS, ag + 64 * K);
         cp_async16(bd, bg);
-        cp_async16(bd + 8 * PBS, bg + 8 * N);
+        cp_async16(bd + (PBK / 2) * PBS, bg + (PBK / 2) * N);
     };
 
     T acc[TM][TN];
@@ -240,17 +250,20 @@ __global__ void __launch_bounds__(kThreads, MINB) matmul_simt_pipe_kernel(T *__r
 #pragma unroll
                         for (int h = 0; h < TN / 2; ++h) fma2(acc2[i][h], a2, b2[h]);
                     }
-                    continue;
+                } else {
+                    T b[TN];  // columns tx*4 .. +3 and 64 + tx*4 .. +3, in 16-byte chunks
+#pragma unroll
+                    for (int c = 0; c < TN / VN; ++c) {
+                        constexpr int half = (TN / VN) / 2;
+                        const BV t = *reinterpret_cast<const BV *>(bs + (kk + k) * PBS + (c < half ? c * VN : 64 + (c - half) * VN));
+#pragma unroll
+                        for (int j = 0; j < VN; ++j) b[c * VN + j] = t.v[j];
+                    }
+#pragma unroll
+                    for (int i = 0; i < TM; ++i)
+#pragma unroll
+                        for (int j = 0; j < TN; ++j) acc[i][j] = mac(acc[i][j], a[i].v[k], b[j]);
                 }
-                const F b0 = *reinterpret_cast<const F *>(bs + (kk + k) * PBS);
-                const F b1 = *reinterpret_cast<const F *>(bs + (kk + k) * PBS + 64);
-                T b[TN];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { b[j] = b0.v[j]; b[4 + j] = b1.v[j]; }
-#pragma unroll
-                for (int i = 0; i < TM; ++i)
-#pragma unroll
-                    for (int j = 0; j < TN; ++j) acc[i][j] = mac(acc[i][j], a[i].v[k], b[j]);
             }
         }
         if (++stage == STAGES) stage = 0;
@@ -282,7 +295,7 @@ template <typename T, int STAGES, int KV, bool F2, int MINB = 2>
 int launch_pipe(feo_ctx *ctx, dim3 grid, T *C, const T *A, const T *B, size_t M, size_t K, size_t N) {
     static bool attr_set[64] = {false};  // the opt-in is per device (and per instantiation)
     const int dev = ctx->device & 63;
-    constexpr int smem = pipe_smem_bytes<STAGES>();
+    constexpr int smem = pipe_smem_bytes<T, STAGES>();
     if (!attr_set[dev]) {
         FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_simt_pipe_kernel<T, STAGES, KV, F2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set[dev] = true;
@@ -300,10 +313,10 @@ int matmul_typed(feo_ctx *ctx, T *C, const T *A, const T *B, size_t M, size_t K,
     if (grid.y > 65535) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "matmul M too large for the SIMT grid");
     const bool fast = (M % BM == 0) && (N % BN == 0) && (K % BK == 0) && feo_aligned16(A) && feo_aligned16(B) && feo_aligned16(C) &&
                       (sizeof(T) == 4 || ((reinterpret_cast<uintptr_t>(C) & 31u) == 0));
+    // knob MATMUL_SIMT: 0 = auto (cp.async pipeline; f32 with FFMA2), 1 = register double buffering,
+    // 2 = pipeline with scalar FMAs, 3..6 = stage / k-vector / occupancy variants of the auto choice
+    const int v = ctx->knobs[FEO_KNOB_MATMUL_SIMT];
     if constexpr (sizeof(T) == 4) {
-        // knob MATMUL_SIMT: 0 = auto (cp.async pipeline; f32 with FFMA2), 1 = register double buffering,
-        // 2 = pipeline with scalar FMAs, 3..5 = stage / k-vector variants of the auto choice
-        const int v = ctx->knobs[FEO_KNOB_MATMUL_SIMT];
         constexpr bool kF = std::is_same<T, float>::value;
         if (fast && v != 1) {
             switch (v) {
@@ -313,6 +326,15 @@ int matmul_typed(feo_ctx *ctx, T *C, const T *A, const T *B, size_t M, size_t K,
                 case 5: return launch_pipe<T, 5, 4, kF>(ctx, grid, C, A, B, M, K, N);
                 case 6: return launch_pipe<T, 4, 4, kF, 1>(ctx, grid, C, A, B, M, K, N);
                 default: return launch_pipe<T, 4, 4, kF>(ctx, grid, C, A, B, M, K, N);
+            }
+        }
+    } else {
+        // 8-byte types: 128 accumulator registers, one CTA per SM -- eight warps have nothing to hide an exposed load behind
+        if (fast && v != 1) {
+            switch (v) {
+                case 3: return launch_pipe<T, 3, 2, false, 1>(ctx, grid, C, A, B, M, K, N);
+                case 4: return launch_pipe<T, 4, 1, false, 1>(ctx, grid, C, A, B, M, K, N);
+                default: return launch_pipe<T, 4, 2, false, 1>(ctx, grid, C, A, B, M, K, N);
             }
         }
     }

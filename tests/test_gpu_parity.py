@@ -645,15 +645,17 @@ def test_matmul_simt_vs_oracle(feo, oracle, dt):
 
 
 def test_matmul_simt_pipeline_variants_agree(feo, oracle):
-    """Aligned 4-byte SIMT matmul: the cp.async pipeline (auto and every stage / k-vector variant) accumulates in the same
+    """Aligned SIMT matmul: the cp.async pipeline (auto and every stage / k-vector variant) accumulates in the same
     per-thread k order as the register-double-buffered kernel, so all of them agree bit for bit -- and with the oracle for
     integers.  Sizes cover fewer k-panels than pipeline stages, a single panel, and many tiles."""
     import feotensor_b200._lib as L
     ctx = feo.Context.default()
     rng = np.random.default_rng(601)
     try:
-        for dt in ("f32", "i32", "u32"):
-            for m, k, n in ((128, 16, 128), (128, 32, 256), (256, 48, 128), (384, 1024, 256), (1024, 512, 640)):
+        for dt in ("f32", "i32", "u32", "f64", "i64"):
+            for m, k, n in ((128, 16, 128), (128, 32, 256), (256, 48, 128), (384, 1024, 256), (1024, 512, 640), (128, 8, 128), (256, 24, 384)):
+                if k % 16 and dt in ("f32", "i32", "u32"):
+                    continue  # 4-byte panels are 16 deep: these shapes take the guarded kernel anyway
                 A, B = rand(oracle, rng, dt, (m, k)), rand(oracle, rng, dt, (k, n))
                 ta, tb = feo.Matrix(feo.shape(m, k), A), feo.Matrix(feo.shape(k, n), B)
                 ctx.tune(L.KNOB_MATMUL_SIMT, 1)
