@@ -3,7 +3,7 @@
 // C[M,N] = A[M,K] * B[K,N], all dense row-major.  128x128 block tile, 8x8 register tile per thread
 // (256 threads), BK-deep shared-memory panels double-buffered through registers, 128-bit global and
 // shared accesses on the aligned fast path and guarded scalar accesses on ragged shapes; aligned shapes
-// take the cp.async-pipelined kernel further down (f32 with packed FFMA2); so do aligned 8-byte types.
+// of every dtype take the cp.async-pipelined kernel further down (f32 with packed FFMA2).
 // Floats accumulate with FMA in k order per thread (reassociation-free along k, but fused: within the
 // stated tolerance of the reference's separate multiply and add); integers wrap, hence bit-exact.
 // Bound: the FP32 pipe (2*M*N*K flop); this is the parity workhorse and the comparison point for
