@@ -152,3 +152,16 @@ def test_flat_index_magic_division_is_exact_below_2_31():
         t = (n * np.uint64(mul)) >> np.uint64(32)
         q = ((t + n) & np.uint64(0xFFFFFFFF)) >> np.uint64(sh)
         np.testing.assert_array_equal(q, n // np.uint64(d), err_msg=f"d={d}")
+
+
+def test_tuning_knobs_agree_between_the_library_and_the_python_mirror():
+    """The knob numbers are part of the (experimental) ABI: csrc/feo_common.cuh's enum and _lib.py must list the same ones."""
+    import feotensor_b200._lib as L
+    text = open(os.path.join(ROOT, "feotensor_b200", "csrc", "feo_common.cuh")).read()
+    body = text[text.index("enum feo_knob {"):]
+    body = body[:body.index("};")]
+    enum = {name: int(val) for name, val in re.findall(r"FEO_(KNOB_[A-Z0-9_]+)\s*=\s*(\d+)", body)}
+    count = enum.pop("KNOB_COUNT")
+    assert sorted(enum.values()) == list(range(count)), "knob numbers are dense"
+    mirror = {k: v for k, v in vars(L).items() if k.startswith("KNOB_")}
+    assert mirror == enum
