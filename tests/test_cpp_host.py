@@ -69,3 +69,11 @@ def test_cpp_port_of_reference_tests_passes_on_gpu():
     sys.stdout.write(out.stdout[-2000:])
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "0 failures" in out.stdout
+
+
+def test_call_overhead_tool_compiles_and_links(tmp_path):
+    """tools/call_overhead.cpp (per-call cost of the C ABI from a compiled host) builds against the in-tree library."""
+    exe = tmp_path / "call_overhead"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "call_overhead.cpp"),
+                    "-L" + LIBDIR, "-lfeotensor_b200", "-Wl,-rpath," + LIBDIR, "-o", str(exe)], check=True)
+    assert os.access(exe, os.X_OK)
