@@ -319,17 +319,57 @@ def run_suite(torch, feo, L, ctx, hbm_peak, tf_peak):
     return suite
 
 
+class Parity:
+    """Bookkeeping of the oracle checks that run inside the sharded suite (the checker is oracle/; nothing here is timed).
+    Every rank checks its own local / replicated result; an entry's `parity_ok` is the AND over the ranks."""
+
+    def __init__(self, torch, dist):
+        self.torch, self.dist = torch, dist
+        self.checks, self.failures = 0, []
+        self._mark = (0, 0)
+
+    def expect(self, cond, what):
+        self.checks += 1
+        if not bool(cond):
+            self.failures.append(what)
+
+    def begin(self):
+        self._mark = (self.checks, len(self.failures))
+
+    def end(self):
+        """(ok over all ranks, number of checks this rank ran since begin())."""
+        ok = 1 if len(self.failures) == self._mark[1] else 0
+        t = self.torch.tensor([ok], device="cuda", dtype=self.torch.int32)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(int(t.item())), self.checks - self._mark[0]
+
+
+def _gamma(n):
+    nu = n * 2.0 ** -24
+    return nu / (1 - nu)
+
+
 def run_suite_sharded(torch, dist, feo, ctx, rank, world, hbm_peak, iters=10):
     """The configs that need an exchange, sharded on the leading axis over `world` GPUs (strong scaling of the BASELINE
     shapes): local kernels + the library's own peer-memory exchange kernels (csrc/peer.cu).  Whole-job figures, timed
-    with CUDA events on the launching stream, max over ranks."""
+    with CUDA events on the launching stream, max over ranks.  After the timing every entry is CHECKED on every rank
+    against the oracle (the reference's arithmetic: tensor.rs:70-322, vector.rs:71-78, matrix.rs:76-90): integers and
+    max/min bit for bit, floats inside the SURVEY 8(d) reassociation bound; `parity_ok` is per entry."""
+    import zlib
+
     import numpy as np
 
+    import feotensor_b200._lib as L
     from feotensor_b200 import sharded
+    from oracle import feo_oracle as oracle  # checker only: runs after the timed regions
+    oracle.lib()
     comm = sharded.PeerComm(ctx)
     eng = sharded.CudaEngine(ctx, comm=comm)
     stream = torch.cuda.current_stream()
     out = {}
+    par = Parity(torch, dist)
+    vp = C.c_void_p
+    lib, h = ctx.lib, ctx.handle
 
     def timed_ms(fn, n=iters):
         for _ in range(3):
@@ -347,38 +387,241 @@ def run_suite_sharded(torch, dist, feo, ctx, rank, world, hbm_peak, iters=10):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # C3 [16384,16384,8] f32, rows split over the ranks
+    def same_on_every_rank(arr, what):
+        crcs = [None] * world
+        dist.all_gather_object(crcs, zlib.crc32(np.ascontiguousarray(arr).tobytes()))
+        par.expect(len(set(crcs)) == 1, f"{what}: replicated result differs across ranks")
+
+    def close(entry):
+        ok, n = par.end()
+        entry["parity_ok"], entry["parity_checks"] = ok, n
+
+    rng = np.random.default_rng(1000 + rank)
+
+    # ---- C3 [16384,16384,8], rows split over the ranks ----------------------------------------------------------
     g3 = [16384, 16384, 8]
-    l3 = [g3[0] // world] + g3[1:]
+    R0, K1, L3 = g3
+    rl = R0 // world
+    l3 = [rl] + g3[1:]
     n_local = int(np.prod(l3))
+
+    def gather_c3(dt, seed, lo, hi, axes, picks):
+        """Host copies (oracle's generator twin) of the reduced slices for the sampled output positions."""
+        cols = []
+        for pk in picks:
+            if axes == [0]:
+                j, l = pk
+                cols.append(oracle.fill_uniform(dt, R0, seed, j * L3 + l, lo, hi, stride=K1 * L3))
+            elif axes == [0, 2]:
+                j = pk
+                cols.append(np.stack([oracle.fill_uniform(dt, R0, seed, j * L3 + l, lo, hi, stride=K1 * L3) for l in range(L3)], axis=1).reshape(-1))
+            elif axes == [2]:
+                i, j = pk
+                cols.append(oracle.fill_uniform(dt, L3, seed, ((rank * rl + i) * K1 + j) * L3, lo, hi))
+            elif axes == [1, 2]:
+                cols.append(oracle.fill_uniform(dt, K1 * L3, seed, (rank * rl + pk) * K1 * L3, lo, hi))
+        return cols
+
+    def picks_for(axes, n):
+        if axes == [0]:
+            return [(int(rng.integers(K1)), int(rng.integers(L3))) for _ in range(n)]
+        if axes == [0, 2]:
+            return [int(rng.integers(K1)) for _ in range(n)]
+        if axes == [2]:
+            return [(int(rng.integers(rl)), int(rng.integers(K1))) for _ in range(n)]
+        return [int(rng.integers(rl)) for _ in range(n)]
+
+    def flat_index(axes, pk):
+        if axes == [0]:
+            return pk[0] * L3 + pk[1]
+        if axes == [2]:
+            return pk[0] * K1 + pk[1]
+        return pk
+
+    def check_c3(kind, axes, res, dt, seed, lo, hi, what, cache):
+        """res: replicated Tensor (0 in axes) or ShardedTensor (local block).  Sampled outputs vs the oracle."""
+        t = res.local if isinstance(res, sharded.ShardedTensor) else res
+        if axes == [0, 1, 2]:
+            v = t.to_numpy()
+            same_on_every_rank(v, what)
+            cache[(kind, "all")] = v[0]
+            return
+        vals = t.to_numpy().reshape(-1) if t.size() <= (1 << 22) else None
+        if not isinstance(res, sharded.ShardedTensor):
+            same_on_every_rank(vals if vals is not None else t.data[0:4096], what)
+            cache[(kind, tuple(axes))] = vals
+        picks = picks_for(axes, 8 if axes != [1, 2] else 3)
+        for pk, col in zip(picks, gather_c3(dt, seed, lo, hi, axes, picks)):
+            fi = flat_index(axes, pk)
+            got = vals[fi] if vals is not None else t.data[fi]
+            ref = oracle.reduce(kind, col, [0])[0]   # the reference's sequential order over the removed coordinates
+            if dt != "f32" or kind in ("max", "min"):
+                par.expect(got == ref, f"{what} at {pk}: {got} != {ref} (bit-exact)")
+                continue
+            c64 = col.astype(np.float64)
+            n = c64.size
+            if kind == "sum":
+                bound = 2 * _gamma(n) * np.abs(c64).sum()
+                par.expect(abs(float(got) - float(ref)) <= bound and abs(float(got) - c64.sum()) <= bound, f"{what} at {pk}: {got} vs {ref}")
+            elif kind == "mean":
+                bound = 2 * _gamma(n) * np.abs(c64).sum() / n
+                par.expect(abs(float(got) - float(ref)) <= bound + 1e-12, f"{what} at {pk}: {got} vs {ref}")
+            else:  # var: GPU (Welford/Chan) and the oracle's two passes both against the exact value
+                bound = 8 * _gamma(n + 2) * (c64 ** 2).mean()
+                par.expect(abs(float(got) - c64.var()) <= bound and abs(float(got) - float(ref)) <= 2 * bound, f"{what} at {pk}: {got} vs {ref}")
+
+    def check_c3_totals(dt, cache, what):
+        """Full reductions against the [0] results already checked by samples (a checksum of checksums)."""
+        if ("sum", (0,)) in cache and ("sum", "all") in cache:
+            s0 = cache[("sum", (0,))]
+            if dt == "f32":
+                par.expect(abs(float(cache[("sum", "all")]) - float(s0.astype(np.float64).sum())) <= 2e-7 * R0 * K1 * L3, f"{what} total sum vs sum of sum[0]")
+            else:
+                par.expect(cache[("sum", "all")] == np.add.reduce(s0, dtype=s0.dtype), f"{what} total sum (wrapping) vs sum of sum[0]")
+        if ("max", (0,)) in cache and ("max", "all") in cache:
+            par.expect(cache[("max", "all")] == cache[("max", (0,))].max(), f"{what} total max vs max of max[0]")
+        if dt == "f32" and ("var", "all") in cache:
+            par.expect(abs(float(cache[("var", "all")]) - 1.0 / 3.0) < 1e-4, f"{what} total var of uniform[-1,1)")
+
     x = feo.Tensor.uniform(feo.Shape(l3), SEED + 4, dtype="f32", first_index=rank * n_local, ctx=ctx)
     sx = sharded.ShardedTensor(eng, x, g3, rank, world)
+    cache = {}
     for axes in ([0], [2], [0, 2], [1, 2], [0, 1, 2]):
         nout = int(np.prod(sharded.reduce_dims(g3, axes)))
         for kind in ("sum", "var", "max"):
             ms = timed_ms(lambda: sx.reduce(kind, axes))
             gbs = 4.0 * (world * n_local + nout) / ms / 1e6
-            out[f"C3_{kind}_axes{''.join(map(str, axes))}"] = {"ms": round(ms, 4), "GB/s": round(gbs, 1), "frac_hbm_per_gpu": round(gbs / world / hbm_peak, 3),
-                                                             "exchange": 0 in axes}
-    del sx, x
-    # C1 [64,128,256]: latency of local reduction + exchange + epilogue
+            entry = {"ms": round(ms, 4), "GB/s": round(gbs, 1), "frac_hbm_per_gpu": round(gbs / world / hbm_peak, 3), "exchange": 0 in axes}
+            if 0 in axes and nout * 4 * (2 if kind == "var" else 1) <= comm.slot_bytes:
+                # the same sequence with the Python object layer stripped: preallocated output, one C-ABI call per op
+                o_ = torch.empty(nout, dtype=torch.float32, device="cuda")
+                div = np.array([sharded.reduce_divisor(np.float32, g3, axes)], dtype=np.float32)
+                fn = lambda: ctx.check(lib.feo_reduce_sharded(comm.handle, L.KIND_CODES[kind], L.F32, vp(o_.data_ptr()), vp(x.data.ptr), 3,
+                                                              L.sizes(l3), len(axes), L.sizes(axes), div.ctypes.data_as(vp)))
+                ms2 = timed_ms(fn)
+                gbs2 = 4.0 * (world * n_local + nout) / ms2 / 1e6
+                entry.update({"ms_c_abi": round(ms2, 4), "GB/s_c_abi": round(gbs2, 1), "frac_hbm_per_gpu_c_abi": round(gbs2 / world / hbm_peak, 3)})
+                del o_
+            par.begin()
+            check_c3(kind, axes, sx.reduce(kind, axes), "f32", SEED + 4, -1.0, 1.0, f"C3 f32 {kind} {axes}", cache)
+            if axes == [0, 1, 2] and kind == "max":
+                check_c3_totals("f32", cache, "C3 f32")
+            close(entry)
+            out[f"C3_{kind}_axes{''.join(map(str, axes))}"] = entry
+    del sx, x, cache
+    # integer twin of the same shard (not timed): every exchange path bit for bit against the oracle
+    xi = feo.Tensor.uniform(feo.Shape(l3), SEED + 14, lo=-1000, hi=1000, dtype="i32", first_index=rank * n_local, ctx=ctx)
+    sxi = sharded.ShardedTensor(eng, xi, g3, rank, world)
+    cache = {}
+    par.begin()
+    for axes in ([0], [0, 2], [2], [0, 1, 2]):
+        for kind in ("sum", "mean", "var", "max", "min"):
+            check_c3(kind, axes, sxi.reduce(kind, axes), "i32", SEED + 14, -1000, 1000, f"C3 i32 {kind} {axes}", cache)
+    check_c3_totals("i32", cache, "C3 i32")
+    entry = {"note": "i32 twin of the C3 shard through the same exchange kernels, sampled outputs bit-exact vs the oracle; not timed"}
+    close(entry)
+    out["C3_i32_twin"] = entry
+    del sxi, xi, cache
+
+    # ---- C1 [64,128,256]: latency of local reduction + exchange + epilogue; whole output checked -----------------
     if 64 % world == 0:
         g1 = [64, 128, 256]
         l1 = [64 // world, 128, 256]
-        x = feo.Tensor.uniform(feo.Shape(l1), SEED + 5, dtype="f32", first_index=rank * int(np.prod(l1)), ctx=ctx)
+        n1 = int(np.prod(l1))
+        x = feo.Tensor.uniform(feo.Shape(l1), SEED + 5, dtype="f32", first_index=rank * n1, ctx=ctx)
         sx = sharded.ShardedTensor(eng, x, g1, rank, world)
+        xh = oracle.fill_uniform("f32", 64 * 128 * 256, SEED + 5).reshape(g1)
         for kind in ("sum", "mean", "var"):
-            out[f"C1_{kind}_axes02_us"] = round(timed_ms(lambda: sx.reduce(kind, [0, 2]), 50) * 1e3, 2)
+            us = round(timed_ms(lambda: sx.reduce(kind, [0, 2]), 50) * 1e3, 2)
+            o_ = torch.empty(128, dtype=torch.float32, device="cuda")
+            div = np.array([sharded.reduce_divisor(np.float32, g1, [0, 2])], dtype=np.float32)
+            us2 = round(timed_ms(lambda: ctx.check(lib.feo_reduce_sharded(comm.handle, L.KIND_CODES[kind], L.F32, vp(o_.data_ptr()), vp(x.data.ptr), 3,
+                                                                           L.sizes(l1), 2, L.sizes([0, 2]), div.ctypes.data_as(vp))), 50) * 1e3, 2)
+            par.begin()
+            got = sx.reduce(kind, [0, 2]).to_numpy()
+            same_on_every_rank(got, f"C1 {kind}")
+            ref = oracle.reduce(kind, xh, [0, 2])
+            x64 = xh.astype(np.float64)
+            nred = 64 * 256
+            if kind == "var":
+                bound = 8 * _gamma(nred + 2) * (x64 ** 2).mean(axis=(0, 2))
+                par.expect(np.all(np.abs(got - x64.var(axis=(0, 2))) <= bound) and np.all(np.abs(got - ref) <= 2 * bound), "C1 var vs oracle / f64")
+            else:
+                bound = 2 * _gamma(nred) * np.abs(x64).sum(axis=(0, 2)) / (nred if kind == "mean" else 1)
+                par.expect(np.all(np.abs(got - ref) <= bound), f"C1 {kind} vs oracle")
+            entry = {"us": us, "us_c_abi": us2}
+            close(entry)
+            out[f"C1_{kind}_axes02"] = entry
         del sx, x
-    # C5 dot on 1e9 elements, both vectors split
+
+    # ---- C5 outer product 65536 x 65536: a split, b replicated, no exchange (tensor.rs:311-322) -----------------
+    nv = 65536
+    if nv % world == 0:
+        nl = nv // world
+        u = feo.Tensor.uniform(feo.Shape([nl]), SEED + 50, dtype="f32", first_index=rank * nl, ctx=ctx)
+        v = feo.Tensor.uniform(feo.Shape([nv]), SEED + 51, dtype="f32", ctx=ctx)
+        su = sharded.ShardedTensor(eng, u, [nv], rank, world)
+        o_ = torch.empty(nl * nv, dtype=torch.float32, device="cuda")
+        ms = timed_ms(lambda: ctx.check(lib.feo_outer(h, L.F32, vp(o_.data_ptr()), vp(u.data.ptr), nl, vp(v.data.ptr), nv)), 5)
+        del o_
+        gbs = 4.0 * (nv + world * nv + nv * nv) / ms / 1e6
+        entry = {"ms": round(ms, 4), "GB/s": round(gbs, 1), "frac_hbm_per_gpu": round(gbs / world / hbm_peak, 3), "exchange": False}
+        par.begin()
+        res = su.outer(v)
+        par.expect(res.global_dims == [nv, nv] and res.local.shape().dims == [nl, nv], "outer shapes")
+        uh, vh = oracle.fill_uniform("f32", nl, SEED + 50, rank * nl), oracle.fill_uniform("f32", nv, SEED + 51)
+        for i in [0, nl - 1] + [int(r) for r in rng.integers(0, nl, 6)]:
+            par.expect(np.array_equal(res.local.data[i * nv:(i + 1) * nv], oracle.ewise_scalar("mul", vh, uh[i])), f"outer row {i} bit-exact")
+        del res
+        close(entry)
+        out["C5_outer_65536"] = entry
+        del su, u, v
+
+    # ---- C5 dot on 1e9 elements, both vectors split ------------------------------------------------------------
     nd = 1_000_000_000 // world
     p_ = feo.Tensor.uniform(feo.Shape([nd]), SEED + 6, dtype="f32", first_index=rank * nd, ctx=ctx)
     q_ = feo.Tensor.uniform(feo.Shape([nd]), SEED + 7, dtype="f32", first_index=rank * nd, ctx=ctx)
     sp, sq = sharded.ShardedTensor(eng, p_, [nd * world], rank, world), sharded.ShardedTensor(eng, q_, [nd * world], rank, world)
     ms = timed_ms(lambda: sp.dot(sq))
-    out["C5_dot_1e9"] = {"ms": round(ms, 4), "GB/s": round(8.0 * nd * world / ms / 1e6, 1), "frac_hbm_per_gpu": round(8.0 * nd / ms / 1e6 / hbm_peak, 3)}
-    del sp, sq, p_, q_
-    # C4 8192^3, A (and C) row-sharded; B replicated, or row-sharded with the gather fused into the 3xTF32 pre-pass
+    entry = {"ms": round(ms, 4), "GB/s": round(8.0 * nd * world / ms / 1e6, 1), "frac_hbm_per_gpu": round(8.0 * nd / ms / 1e6 / hbm_peak, 3), "exchange": True}
+    o_ = torch.empty(1, dtype=torch.float32, device="cuda")
+    ms2 = timed_ms(lambda: ctx.check(lib.feo_dot_sharded(comm.handle, L.F32, vp(o_.data_ptr()), vp(p_.data.ptr), vp(q_.data.ptr), 1, nd)))
+    entry.update({"ms_c_abi": round(ms2, 4), "frac_hbm_per_gpu_c_abi": round(8.0 * nd / ms2 / 1e6 / hbm_peak, 3)})
+    par.begin()
+
+    def check_dot(dt, a_t, b_t, seed_a, seed_b, lo, hi, got):
+        same_on_every_rank(got, f"dot {dt}")
+        # a prefix of the local shard against the oracle's sequential dot, then the exchange against the ranks' partials
+        m = 1 << 20
+        ah, bh = oracle.fill_uniform(dt, m, seed_a, rank * nd, lo, hi), oracle.fill_uniform(dt, m, seed_b, rank * nd, lo, hi)
+        pre = torch.empty(1, dtype=torch.float32 if dt == "f32" else torch.int32, device="cuda")
+        ctx.check(lib.feo_dot(h, L.code_of(dt), vp(pre.data_ptr()), vp(a_t.data.ptr), vp(b_t.data.ptr), m))
+        part = torch.empty_like(pre)
+        ctx.check(lib.feo_dot(h, L.code_of(dt), vp(part.data_ptr()), vp(a_t.data.ptr), vp(b_t.data.ptr), nd))
+        torch.cuda.synchronize()
+        parts = [None] * world
+        dist.all_gather_object(parts, part.cpu().numpy()[0])
+        if dt == "f32":
+            e64 = float(ah.astype(np.float64) @ bh.astype(np.float64))
+            t64 = float(np.abs(ah).astype(np.float64) @ np.abs(bh).astype(np.float64))
+            par.expect(abs(float(pre.item()) - e64) <= 2 * _gamma(m) * t64 and abs(float(oracle.dot(ah, bh)[0]) - e64) <= 2 * _gamma(m) * t64, "dot prefix vs oracle / f64")
+            tot = float(sum(float(v_) for v_ in parts))  # the exchange adds the ranks' partials in rank order, in f32
+            par.expect(abs(float(got[0]) - tot) <= world * 2.0 ** -24 * sum(abs(float(v_)) for v_ in parts) + 1e-30, f"dot f32 {got[0]} vs sum of rank partials {tot}")
+        else:
+            par.expect(int(pre.item()) == int(oracle.dot(ah, bh)[0]), "dot i32 prefix bit-exact vs oracle")
+            par.expect(np.int32(got[0]) == np.add.reduce(np.array(parts, dtype=np.int32), dtype=np.int32), "dot i32 exchange bit-exact")
+
+    check_dot("f32", p_, q_, SEED + 6, SEED + 7, -1.0, 1.0, sp.dot(sq).to_numpy())
+    del sp, sq, p_, q_, o_
+    pi = feo.Tensor.uniform(feo.Shape([nd]), SEED + 16, lo=-1000, hi=1000, dtype="i32", first_index=rank * nd, ctx=ctx)
+    qi = feo.Tensor.uniform(feo.Shape([nd]), SEED + 17, lo=-1000, hi=1000, dtype="i32", first_index=rank * nd, ctx=ctx)
+    spi, sqi = sharded.ShardedTensor(eng, pi, [nd * world], rank, world), sharded.ShardedTensor(eng, qi, [nd * world], rank, world)
+    check_dot("i32", pi, qi, SEED + 16, SEED + 17, -1000, 1000, spi.dot(sqi).to_numpy())
+    del spi, sqi, pi, qi
+    close(entry)
+    out["C5_dot_1e9"] = entry
+
+    # ---- C4 8192^3, A (and C) row-sharded; B replicated, or row-sharded with the gather fused into the kernels ----
     n = 8192
     rows_ = n // world
     A = feo.Tensor.uniform(feo.Shape([rows_, n]), SEED + 8, dtype="f32", first_index=rank * rows_ * n, ctx=ctx)
@@ -392,11 +635,31 @@ def run_suite_sharded(torch, dist, feo, ctx, rank, world, hbm_peak, iters=10):
     flop = 2.0 * n * n * n
     for label, fn in (("b_replicated", lambda: sa.matmul(Bfull, algo="tf32x3")), ("b_sharded_fused_gather", lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))):
         ms = timed_ms(fn)
-        out[f"C4_matmul_tf32x3_{label}"] = {"ms": round(ms, 4), "TFLOP/s": round(flop / ms / 1e9, 1)}
+        entry = {"ms": round(ms, 4), "TFLOP/s": round(flop / ms / 1e9, 1)}
+        par.begin()
+        Cl = fn().local
+        rr, cc = rng.integers(0, rows_, 16), rng.integers(0, n, 16)
+        Ar = np.stack([oracle.fill_uniform("f32", n, SEED + 8, (rank * rows_ + int(r)) * n) for r in rr])      # [16, K]
+        Bc = np.stack([oracle.fill_uniform("f32", n, SEED + 9, int(c), stride=n) for c in cc], axis=1)          # [K, 16]
+        ref = oracle.matmul_entries(Ar, Bc, np.arange(16), np.arange(16)).astype(np.float64)                   # the reference's k order
+        exact = np.einsum("ik,ki->i", Ar.astype(np.float64), Bc.astype(np.float64))
+        terms = np.einsum("ik,ki->i", np.abs(Ar).astype(np.float64), np.abs(Bc).astype(np.float64))
+        got = np.array([Cl.data[int(r) * n + int(c)] for r, c in zip(rr, cc)], dtype=np.float64)
+        par.expect(np.all(np.abs(got - ref) <= 2 * _gamma(n + 1) * terms), f"matmul {label} vs oracle k-order")
+        par.expect(np.all(np.abs(got - exact) <= np.maximum(2 * np.abs(ref - exact), 2.0 ** -20 * terms)), f"matmul {label} vs f64")
+        del Cl
+        close(entry)
+        out[f"C4_matmul_tf32x3_{label}"] = entry
     dist.barrier()
     del sa, sb, Bl, A, Bfull
     buf.close()
     comm.close()
+    ok_all = all(e.get("parity_ok", True) for e in out.values() if isinstance(e, dict))
+    fails = [None] * world
+    dist.all_gather_object(fails, par.failures[:8])
+    out["parity_ok"] = ok_all
+    out["parity_checks_rank0"] = par.checks
+    out["parity_failures"] = [f for fl in fails for f in fl][:16]
     return out
 
 
@@ -604,16 +867,16 @@ def main():
         # times out), the headline line measured above must still come out.  A watchdog prints it and ends the process.
         def bail():
             if rank == 0:
-                line["suite_sharded"] = {"error": "timed out after 240 s"}
+                line["suite_sharded"] = {"error": "timed out after 420 s", "parity_ok": False}
                 print(json.dumps(line), flush=True)
             os._exit(0)
-        dog = threading.Timer(240.0, bail)
+        dog = threading.Timer(420.0, bail)
         dog.daemon = True
         dog.start()
         try:
             sharded_suite = run_suite_sharded(torch, dist, feo, ctx, rank, world, hbm_peak)
         except Exception as e:  # collective code: every rank runs it
-            sharded_suite = {"error": repr(e)}
+            sharded_suite = {"error": repr(e), "parity_ok": False}
         dog.cancel()
         line["suite_sharded"] = sharded_suite
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -103,6 +103,17 @@ def run_checks(feo, sharded, o, dist, ctx, eng, rank, world, label, with_gather=
                     np.testing.assert_allclose(g, want, err_msg=msg, **tol)
                     np.testing.assert_allclose(g, single, err_msg=msg, **tol)
                 checks += 1
+        # Tensor::prod (tensor.rs:311-322) with the left operand split and the right one replicated: no exchange, one IEEE
+        # multiply per element -> bit-exact for every dtype
+        u, v = gen(dt, (R * 6,)), gen(dt, (77,))
+        got = sharded.shard_rows(eng, u).outer(feo.Tensor(feo.shape(77), v, ctx=ctx))
+        assert got.global_dims == [R * 6, 77]
+        np.testing.assert_array_equal(got.local.to_numpy(), rows(o.prod(u, v)), err_msg=f"{label} {dt} outer")
+        u2 = gen(dt, (R, 3, 5))
+        got = sharded.shard_rows(eng, u2).outer(feo.Tensor(feo.shape(4, 2), v[:8].reshape(4, 2).copy(), ctx=ctx))
+        assert got.global_dims == [R, 3, 5, 4, 2]
+        np.testing.assert_array_equal(got.local.to_numpy(), rows(o.prod(u2, v[:8].reshape(4, 2))), err_msg=f"{label} {dt} outer 3d x 2d")
+        checks += 2
         p, q = gen(dt, (R * 1000,)), gen(dt, (R * 1000,))
         got = sharded.shard_rows(eng, p).dot(sharded.shard_rows(eng, q)).to_numpy()
         same_on_every_rank(got, f"{dt} dot")
