@@ -18,7 +18,7 @@ F32, F64, I32, I64, U32 = 0, 1, 2, 3, 4
 ADD, SUB, MUL, DIV = 0, 1, 2, 3
 SUM, MEAN, VAR, MAX, MIN = 0, 1, 2, 3, 4
 MATMUL_AUTO, MATMUL_SIMT, MATMUL_TF32X3 = 0, 1, 2
-KNOB_BCAST_TILE, KNOB_REDUCE_SPLIT, KNOB_REDUCE_BLOCKS_PER_SM, KNOB_MATMUL_TF32_KC, KNOB_BCAST_LCHUNK, KNOB_PDL, KNOB_BCAST_L2KEEP, KNOB_REDUCE_FUSE, KNOB_GATHER_OVERLAP, KNOB_MATMUL_SIMT = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
+KNOB_BCAST_TILE, KNOB_REDUCE_SPLIT, KNOB_REDUCE_BLOCKS_PER_SM, KNOB_MATMUL_TF32_KC, KNOB_BCAST_LCHUNK, KNOB_PDL, KNOB_BCAST_L2KEEP, KNOB_REDUCE_FUSE, KNOB_GATHER_OVERLAP, KNOB_MATMUL_SIMT, KNOB_PEER_TIMEOUT_S = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 MAX_RANK = 8
 
 DTYPE_CODES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32,
@@ -85,6 +85,7 @@ SIGNATURES = {
     "feo_comm_create": (_int, [_vp, _int, _int, C.POINTER(_vp), _sz, C.POINTER(_vp)]),
     "feo_comm_destroy": (_int, [_vp]),
     "feo_comm_slot": (_int, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
+    "feo_peer_status": (_int, [_vp, C.POINTER(_int), _int]),
     "feo_comm_barrier": (_int, [_vp]),
     "feo_comm_allreduce": (_int, [_vp, _int, _int, _vp, _sz, _sz, _vp]),
     "feo_reduce_sharded": (_int, [_vp, _int, _int, _vp, _vp, _int, _szp, _int, _szp, _vp]),

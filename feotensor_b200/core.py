@@ -71,6 +71,8 @@ class Context:
         msg = (self.lib.feo_last_error(self.handle) or b"").decode()
         if rc == L.ERR_SHAPE:
             raise ShapeError(msg)
+        if rc == L.ERR_ARITH:  # integer x/0 or MIN/-1: the reference panics (at the operator; here at the next sync point)
+            raise ReferencePanic(msg)
         raise BackendError(f"status {rc}: {msg}")
 
     # memory

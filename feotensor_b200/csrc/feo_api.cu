@@ -2,6 +2,7 @@
 // argument validation in front of the sm_100a kernels.  See include/feotensor_b200.h for the
 // reference function (file:line) each entry point replaces.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "feo_common.cuh"
@@ -66,6 +67,25 @@ int feo_workspace(feo_ctx *ctx, size_t bytes, void **ptr) {
     return FEO_OK;
 }
 
+// The synchronisation points (feo_sync, feo_download) are where the sticky device flags reach the host: the reference panics
+// at `a / b` itself (integer x/0, MIN/-1); an asynchronous backend reports it at the next point the host looks at results.
+static int feo_sync_and_check(feo_ctx *ctx) {
+    if (ctx->host_flags) FEO_CUDA(ctx, cudaMemcpyAsync(ctx->host_flags, ctx->arith_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FEO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!ctx->host_flags) return FEO_OK;
+    if (ctx->host_flags[0]) {
+        FEO_CUDA(ctx, cudaMemsetAsync(ctx->arith_flag, 0, sizeof(int), ctx->stream));
+        return feo_fail(ctx, FEO_ERR_ARITH, "attempt to divide by zero, or to divide with overflow, in an integer kernel since the last "
+                                            "synchronisation (the reference panics; the kernel wrote 0 there)");
+    }
+    if (ctx->host_flags[1]) {
+        FEO_CUDA(ctx, cudaMemsetAsync(ctx->status_flag, 0, sizeof(int), ctx->stream));
+        return feo_fail(ctx, FEO_ERR_CUDA, "a kernel gave up waiting for a peer rank after %.0f s: the results of that exchange are invalid",
+                        ctx->peer_timeout_ns * 1e-9);
+    }
+    return FEO_OK;
+}
+
 extern "C" {
 
 int feo_abi_version(void) { return FEO_ABI_VERSION; }
@@ -107,10 +127,16 @@ int feo_init(int device, feo_ctx **out) {
             cudaGetLastError();
         }
     }
-    if (cudaMalloc(&ctx->arith_flag, sizeof(int)) != cudaSuccess || cudaMemset(ctx->arith_flag, 0, sizeof(int)) != cudaSuccess) {
+    if (cudaMalloc(&ctx->arith_flag, 2 * sizeof(int)) != cudaSuccess || cudaMemset(ctx->arith_flag, 0, 2 * sizeof(int)) != cudaSuccess) {
         cudaStreamDestroy(ctx->own_stream);
         delete ctx;
         return FEO_ERR_CUDA;
+    }
+    ctx->status_flag = ctx->arith_flag + 1;
+    if (cudaMallocHost(&ctx->host_flags, 2 * sizeof(int)) != cudaSuccess) { ctx->host_flags = nullptr; cudaGetLastError(); }
+    if (const char *env = getenv("FEO_PEER_TIMEOUT_S")) {
+        const double sec = atof(env);
+        ctx->peer_timeout_ns = sec > 0 ? (unsigned long long)(sec * 1e9) : 0;
     }
     ctx->counters_len = size_t(1) << 20;
     if (cudaMalloc(&ctx->counters, ctx->counters_len * sizeof(unsigned int)) != cudaSuccess ||
@@ -131,6 +157,7 @@ int feo_shutdown(feo_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->arith_flag) cudaFree(ctx->arith_flag);
+    if (ctx->host_flags) cudaFreeHost(ctx->host_flags);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -153,13 +180,14 @@ int feo_set_stream(feo_ctx *ctx, void *s) {
 void *feo_get_stream(feo_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 int feo_sync(feo_ctx *ctx) {
     FEO_ENTER(ctx);
-    FEO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return FEO_OK;
+    if (!ctx) return FEO_ERR_SHAPE;
+    return feo_sync_and_check(ctx);
 }
 uint64_t feo_launch_count(feo_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int feo_tune(feo_ctx *ctx, int knob, int value) {
     if (!ctx || knob < 0 || knob >= FEO_KNOB_COUNT) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "unknown knob %d", knob);
     ctx->knobs[knob] = value;
+    if (knob == FEO_KNOB_PEER_TIMEOUT_S) ctx->peer_timeout_ns = value > 0 ? (unsigned long long)value * 1000000000ull : 0;
     return FEO_OK;
 }
 
@@ -206,8 +234,7 @@ int feo_download(feo_ctx *ctx, void *dst, const void *src, size_t bytes) {
     FEO_ENTER(ctx);
     int rc = feo_download_async(ctx, dst, src, bytes);
     if (rc != FEO_OK) return rc;
-    FEO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return FEO_OK;
+    return feo_sync_and_check(ctx);  // the data is copied either way; FEO_ERR_ARITH says it contains the zeros of a x/0
 }
 int feo_copy(feo_ctx *ctx, void *dst, const void *src, size_t bytes) {
     FEO_ENTER(ctx);
@@ -297,6 +324,12 @@ int feo_ewise_scalar(feo_ctx *ctx, int op, int dtype, void *out, const void *a, 
     if (!ctx || !out || !a || !scalar_host) return feo_fail(ctx, FEO_ERR_SHAPE, "null argument");
     if (op < FEO_ADD || op > FEO_DIV) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "unknown op %d", op);
     if (n == 0) return FEO_OK;
+    if (op == FEO_DIV) {  // `tensor / 0` on an integer tensor panics in the reference at the first element (tensor.rs:465-475)
+        bool zero = false;
+        if (dtype == FEO_I32 || dtype == FEO_U32) zero = *static_cast<const uint32_t *>(scalar_host) == 0;
+        else if (dtype == FEO_I64) zero = *static_cast<const int64_t *>(scalar_host) == 0;
+        if (zero) return feo_fail(ctx, FEO_ERR_ARITH, "attempt to divide by zero");
+    }
     return feo_impl_ewise(ctx, op, dtype, out, a, nullptr, scalar_host, n);
 }
 int feo_pow(feo_ctx *ctx, int dtype, void *out, const void *a, const void *power_host, size_t n) {
@@ -322,6 +355,19 @@ int feo_arith_flag(feo_ctx *ctx, int *flag, int clear) {
     FEO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (flag) *flag = v;
     if (clear) FEO_CUDA(ctx, cudaMemsetAsync(ctx->arith_flag, 0, sizeof(int), ctx->stream));
+    return FEO_OK;
+}
+
+int feo_peer_status(feo_ctx *ctx, int *timed_out, int clear) {
+    FEO_ENTER(ctx);
+    if (!ctx) return FEO_ERR_SHAPE;
+    int v = 0;
+    FEO_CUDA(ctx, cudaMemcpyAsync(&v, ctx->status_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FEO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (timed_out) *timed_out = v & 1;
+    if (clear) FEO_CUDA(ctx, cudaMemsetAsync(ctx->status_flag, 0, sizeof(int), ctx->stream));
+    if (v & 1) return feo_fail(ctx, FEO_ERR_CUDA, "a kernel gave up waiting for a peer rank after %.0f s: the results of that exchange are invalid",
+                               ctx->peer_timeout_ns * 1e-9);
     return FEO_OK;
 }
 

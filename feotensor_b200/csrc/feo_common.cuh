@@ -24,7 +24,8 @@ enum feo_knob {
     FEO_KNOB_REDUCE_FUSE = 7,   // split reductions: last-arriving CTA combines the partials in the same launch: 0 = auto (small inputs), 1 = off, 2 = always
     FEO_KNOB_GATHER_OVERLAP = 8,  // sharded-B matmul: pull B's panels on a side stream while the matmul kernel runs: 0 = on, 1 = off
     FEO_KNOB_MATMUL_SIMT = 9,   // SIMT matmul, aligned 4-byte types: 0 = auto (cp.async pipeline), 1 = register double buffering, 2..5 = pipeline variants
-    FEO_KNOB_COUNT = 10
+    FEO_KNOB_PEER_TIMEOUT_S = 10,  // seconds a kernel waits for a peer before it raises the status flag and goes on (0 = for ever); default: FEO_PEER_TIMEOUT_S or 600
+    FEO_KNOB_COUNT = 11
 };
 
 // Address ranges of a launch, for the hazard check that lets independent back-to-back kernels overlap their tails.
@@ -42,6 +43,9 @@ struct feo_ctx {
     void *workspace = nullptr;          // scratch for two-stage reductions
     size_t workspace_bytes = 0;
     int *arith_flag = nullptr;          // device int, sticky
+    int *host_flags = nullptr;          // pinned [2]: where feo_sync / feo_download read arith_flag and status_flag into
+    int *status_flag = nullptr;         // device int, sticky: feo_peer::kStatusPeerTimeout (arith_flag + 1)
+    unsigned long long peer_timeout_ns = 600ull * 1000000000ull;
     unsigned int *counters = nullptr;   // zeroed arrival counters for the fused reduction combine
     size_t counters_len = 0;
     uint64_t launches = 0;
@@ -140,6 +144,20 @@ template <int OP, typename T> __device__ __forceinline__ T apply_op(T a, T b, in
     else if constexpr (OP == FEO_SUB) return w_sub(a, b);
     else if constexpr (OP == FEO_MUL) return w_mul(a, b);
     else return w_div(a, b, flag);
+}
+
+// max / min of two values as the reductions use them (tensor.rs:248, :300 replace on a strict compare).  Floats go through
+// fmax / fmin (one FMNMX): the result is one of the operands, and a NaN operand never wins -- the reference's strict
+// compares skip NaN elements too -- and never swallows the other operand of a tree node either.
+template <typename T> __device__ __forceinline__ T feo_max2(T a, T b) {
+    if constexpr (std::is_same<T, float>::value) return fmaxf(a, b);
+    else if constexpr (std::is_same<T, double>::value) return fmax(a, b);
+    else return (b > a) ? b : a;
+}
+template <typename T> __device__ __forceinline__ T feo_min2(T a, T b) {
+    if constexpr (std::is_same<T, float>::value) return fminf(a, b);
+    else if constexpr (std::is_same<T, double>::value) return fmin(a, b);
+    else return (b < a) ? b : a;
 }
 
 // ---- 128-bit (and narrower) vector access ---------------------------------------------------------

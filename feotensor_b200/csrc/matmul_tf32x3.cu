@@ -54,8 +54,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded wait: a pipeline bug traps (and reports) after 30 s instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int what) {
+// Bounded wait (limit_ns = 0: unbounded): the pipeline's barriers complete within microseconds unless the producer is itself
+// waiting for a peer's k-blocks, and that wait gives up after the context's peer timeout -- so a barrier still closed after
+// twice that plus a margin is a pipeline bug, and the only sane reaction is to report and trap instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int what, unsigned long long limit_ns) {
     const uint32_t addr = smem_u32(bar);
     unsigned long long t_start = 0;
     for (uint32_t spin = 0;; ++spin) {
@@ -68,11 +70,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int wh
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) return;
-        // With B arriving from other GPUs the pipeline legitimately waits for a late peer, so the bound is wall time
-        // (the same 30 s as the exchange flags), sampled every 2^20 polls.
-        if ((spin & 0xFFFFFu) == 0xFFFFFu) {
+        // wall time, sampled every 2^20 polls
+        if (limit_ns != 0 && (spin & 0xFFFFFu) == 0xFFFFFu) {
             if (t_start == 0) t_start = feo_peer::global_ns();
-            else if (feo_peer::global_ns() - t_start > feo_peer::kWaitNs) {
+            else if (feo_peer::global_ns() - t_start > limit_ns) {
                 printf("matmul_tf32x3: mbarrier wait timed out (what=%d block=%d thread=%d parity=%u)\n", what, blockIdx.x, threadIdx.x, parity);
                 __trap();
             }
@@ -114,7 +115,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 matmul_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                      float *__restrict__ C, int M, int N, int num_k_blocks, int kc, const unsigned int *__restrict__ ready,
-                     unsigned int ready_need, int kb_rot) {
+                     unsigned int ready_need, int kb_rot, unsigned long long peer_timeout_ns, int *status) {
+    const unsigned long long bar_limit = peer_timeout_ns ? 2 * peer_timeout_ns + 30000000000ull : 0;
     // `ready` != nullptr: Bt's k-blocks are still being produced by the gathering pre-pass running concurrently on another
     // stream; ready[kb] counts its finished CTAs (ready_need per k-block).  Iteration i works on k-block (i + kb_rot) % n,
     // the order the pre-pass fills them in (the local panel first, then the peers' in ring order).
@@ -177,9 +179,12 @@ matmul_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     const unsigned int mask = __ballot_sync(0xffffffffu, ok);
                     const int prefix = __ffs(~mask) - 1;  // number of leading ready iterations (32 if all)
                     if (prefix != 0) { ready_upto = it + (prefix < 0 ? 32 : prefix); break; }
-                    if (feo_peer::global_ns() - t0 > 10ull * 1000 * 1000 * 1000) {
-                        if (lane == 0) printf("matmul_tf32x3: k-block %d of B never arrived (block %d)\n", it, blockIdx.x);
-                        __trap();
+                    if (peer_timeout_ns != 0 && feo_peer::global_ns() - t0 > peer_timeout_ns) {
+                        // a peer never delivered its panel: raise the status flag and finish on whatever is there
+                        if (lane == 0 && atomicOr(status, feo_peer::kStatusPeerTimeout) == 0)
+                            printf("matmul_tf32x3: k-block %d of B never arrived (block %d); result invalid\n", it, blockIdx.x);
+                        ready_upto = num_k_blocks;
+                        break;
                     }
                     __nanosleep(100);
                 }
@@ -190,7 +195,7 @@ matmul_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 if (kb >= num_k_blocks) kb -= num_k_blocks;
                 const int s = it % kStages;
                 const uint32_t ph = (it / kStages) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1, 0);
+                mbar_wait(&empty_bar[s], ph ^ 1, 0, bar_limit);
                 uint8_t *st = smem + s * kStageBytes;
                 mbar_expect_tx(&full_bar[s], kStageBytes);
                 tma_load_2d(st, &map_a_hi, &full_bar[s], kb * BK, m0);
@@ -205,14 +210,14 @@ matmul_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             int kb = 0;
             for (int c = 0; c < num_chunks; ++c) {
                 const int buf = c & 1;
-                mbar_wait(&tmem_empty_bar[buf], ((c >> 1) & 1) ^ 1, 3);  // the epilogue has drained this buffer
+                mbar_wait(&tmem_empty_bar[buf], ((c >> 1) & 1) ^ 1, 3, bar_limit);  // the epilogue has drained this buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
                 const int kb_end = (kb + kc < num_k_blocks) ? kb + kc : num_k_blocks;
                 for (int first = 1; kb < kb_end; ++kb) {
                     const int s = kb % kStages;
                     const uint32_t ph = (kb / kStages) & 1;
-                    mbar_wait(&full_bar[s], ph, 1);
+                    mbar_wait(&full_bar[s], ph, 1, bar_limit);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st = smem_u32(smem + s * kStageBytes);
                     const uint64_t da_hi = make_desc(st), da_lo = make_desc(st + kTileABytes);
@@ -238,7 +243,7 @@ matmul_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         for (int i = 0; i < BN / 2; ++i) acc[i] = 0.f;
         for (int c = 0; c < num_chunks; ++c) {
             const int buf = c & 1;
-            mbar_wait(&tmem_full_bar[buf], (c >> 1) & 1, 2);
+            mbar_wait(&tmem_full_bar[buf], (c >> 1) & 1, 2, bar_limit);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int j = 0; j < BN / 2; j += 32) {
@@ -499,7 +504,7 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
     int kc = ctx->knobs[FEO_KNOB_MATMUL_TF32_KC];
     if (kc <= 0) kc = 2;  // k-blocks per TMEM accumulation chain (24 truncating accumulates), see the file header
     matmul_tf32x3_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, (float *)C, (int)M, (int)N, num_kb, kc, ready,
-                                                                      (unsigned)feo_ceil_div(N, (size_t)GT_N), kb_rot);
+                                                                      (unsigned)feo_ceil_div(N, (size_t)GT_N), kb_rot, ctx->peer_timeout_ns, ctx->status_flag);
     FEO_LAUNCH_CHECK(ctx);
     if (overlap) FEO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // the workspace is reused by the next call
     return FEO_OK;

@@ -10,7 +10,7 @@
 //   1. the local kernels (feo_reduce_partial, feo_dot, ...) write this rank's partial straight into slot e & 1 of the
 //      rank's OWN window -- no staging copy;
 //   2. the exchange kernel stores e into flag[rank] of every peer's window (st.release.sys), polls its own flags until all
-//      ranks have reached e (ld.acquire.sys, bounded: a peer that never arrives traps after kWaitNs instead of hanging),
+//      ranks have reached e (ld.acquire.sys; bounded by the context's peer timeout: on expiry the status flag is raised, see peer_sync.cuh),
 //   3. then every thread loads its elements of all `world` partials (the remote ones are plain peer loads over
 //      NVLink/NVSwitch), combines them in RANK ORDER -- so the result is deterministic and bit-identical on every rank --
 //      and applies the epilogue of the reference operation (mean: / n; var: Chan merge, / n) before the one store.
@@ -31,8 +31,8 @@ namespace {
 enum { X_SUM = 0, X_MEAN = 1, X_VAR = 2, X_MAX = 3, X_MIN = 4 };
 
 template <typename T, int KIND> __device__ __forceinline__ T combine2(T a, T b) {
-    if constexpr (KIND == X_MAX) return b > a ? b : a;
-    else if constexpr (KIND == X_MIN) return b < a ? b : a;
+    if constexpr (KIND == X_MAX) return feo_max2(a, b);
+    else if constexpr (KIND == X_MIN) return feo_min2(a, b);
     else return w_add(a, b);
 }
 
@@ -153,6 +153,8 @@ XchgParams next_exchange(feo_comm *comm, long long n) {
     p.epoch = ++comm->epoch;
     p.slot_off = kFlagBytes + (p.epoch & 1) * comm->slot_bytes;
     p.n = n;
+    p.timeout_ns = comm->ctx->peer_timeout_ns;
+    p.status = comm->ctx->status_flag;
     return p;
 }
 

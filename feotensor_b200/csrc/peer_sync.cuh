@@ -17,7 +17,12 @@ namespace feo_peer {
 constexpr int kMaxPeers = FEO_MAX_PEERS;
 constexpr size_t kFlagStride = 128;
 constexpr size_t kFlagBytes = kMaxPeers * kFlagStride;
-constexpr unsigned long long kWaitNs = 30ull * 1000 * 1000 * 1000;  // a peer 30 s late is a dead peer
+// How long a kernel waits for a peer is ONE setting for every device-side wait (exchange flags, the sharded matmul's
+// k-block flags, and -- with a margin on top -- the matmul's own pipeline barriers): feo_ctx::peer_timeout_ns, from the
+// environment variable FEO_PEER_TIMEOUT_S or feo_tune(FEO_KNOB_PEER_TIMEOUT_S) (default 600 s; 0 = wait for ever, like a
+// collective library).  A wait that expires raises FEO_STATUS_PEER_TIMEOUT in the context's status word and the kernel goes
+// on with whatever data is there: the context stays usable, and the host finds out at feo_peer_status / feo_sync.
+constexpr int kStatusPeerTimeout = 1;
 constexpr int kXThreads = 256;
 
 struct XchgParams {
@@ -26,6 +31,8 @@ struct XchgParams {
     unsigned long long epoch;
     size_t slot_off;
     long long n;  // outputs
+    unsigned long long timeout_ns;  // 0 = no bound
+    int *status;                    // device status word of the context (kStatusPeerTimeout on expiry)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -69,10 +76,11 @@ __device__ __forceinline__ void signal_and_wait(const XchgParams &p) {
         const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(p.win[p.rank] + threadIdx.x * kFlagStride);
         const unsigned long long t0 = global_ns();
         while (ld_acquire_sys(mine) < p.epoch) {
-            if (global_ns() - t0 > kWaitNs) {
-                printf("feo peer exchange: rank %d waited 30 s for rank %d to reach exchange %llu (it is at %llu)\n", p.rank, (int)threadIdx.x,
-                       p.epoch, ld_acquire_sys(mine));
-                __trap();
+            if (p.timeout_ns != 0 && global_ns() - t0 > p.timeout_ns) {
+                if (p.status && atomicOr(p.status, kStatusPeerTimeout) == 0)
+                    printf("feo peer exchange: rank %d gave up waiting for rank %d to reach exchange %llu (it is at %llu); result invalid\n",
+                           p.rank, (int)threadIdx.x, p.epoch, ld_acquire_sys(mine));
+                break;
             }
             __nanosleep(32);
         }

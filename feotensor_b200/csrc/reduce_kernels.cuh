@@ -63,10 +63,16 @@ template <typename T> struct Acc<T, K_SQDEV> {  // sum of (x - mean)^2 for a giv
 };
 template <typename T> struct Acc<T, K_MAX> {
     T v;
-    __device__ __forceinline__ void init(T) { v = std::numeric_limits<T>::lowest(); }
-    __device__ __forceinline__ void push(T x) { v = (x > v) ? x : v; }  // strict compare, tensor.rs:248
+    // Seed: the identity of max.  Floats start at -inf, so a slice of -inf reduces to -inf exactly like the reference, whose
+    // init min(0, every x) (tensor.rs:234-237) is <= every element.  NaN never wins the strict compare (as in tensor.rs:248);
+    // the reference's order-dependent NaN handling in its init fold is not reproduced (unspecified).
+    __device__ __forceinline__ void init(T) {
+        if constexpr (std::is_floating_point<T>::value) v = -std::numeric_limits<T>::infinity();
+        else v = std::numeric_limits<T>::lowest();
+    }
+    __device__ __forceinline__ void push(T x) { v = feo_max2(v, x); }  // replace on a strict compare, tensor.rs:248
     __device__ __forceinline__ void merge(const Acc &o) { push(o.v); }
-    static __device__ __forceinline__ T pick(T a, T b) { return (b > a) ? b : a; }
+    static __device__ __forceinline__ T pick(T a, T b) { return feo_max2(a, b); }
     // Batches are combined as a balanced tree: short dependency chains, and every load of the batch is needed by the
     // first level, so the scheduler keeps the loads grouped ahead of the arithmetic (a serial chain made ptxas sink each
     // load next to its use: one load in flight per thread, -20 % on the rows kernel).
@@ -88,10 +94,13 @@ template <typename T> struct Acc<T, K_MAX> {
 };
 template <typename T> struct Acc<T, K_MIN> {
     T v;
-    __device__ __forceinline__ void init(T) { v = std::numeric_limits<T>::max(); }
-    __device__ __forceinline__ void push(T x) { v = (x < v) ? x : v; }  // tensor.rs:300
+    __device__ __forceinline__ void init(T) {  // +inf for floats: see K_MAX
+        if constexpr (std::is_floating_point<T>::value) v = std::numeric_limits<T>::infinity();
+        else v = std::numeric_limits<T>::max();
+    }
+    __device__ __forceinline__ void push(T x) { v = feo_min2(v, x); }  // tensor.rs:300
     __device__ __forceinline__ void merge(const Acc &o) { push(o.v); }
-    static __device__ __forceinline__ T pick(T a, T b) { return (b < a) ? b : a; }
+    static __device__ __forceinline__ T pick(T a, T b) { return feo_min2(a, b); }
     // Batches are combined as a balanced tree: short dependency chains, and every load of the batch is needed by the
     // first level, so the scheduler keeps the loads grouped ahead of the arithmetic (a serial chain made ptxas sink each
     // load next to its use: one load in flight per thread, -20 % on the rows kernel).

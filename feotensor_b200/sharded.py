@@ -82,8 +82,14 @@ class PeerComm:
     def barrier(self):
         self.ctx.check(self.lib.feo_comm_barrier(self.handle))
 
-    def close(self):
+    def close(self, barrier=True):
+        """Collective: every rank calls it.  A slower rank may still be inside the last exchange kernel, loading this
+        rank's slot or storing its flag into this window, so the ranks meet in one more barrier kernel before anyone
+        unmaps or frees anything (barrier=False: the caller has already made sure of that, e.g. several ranks driven by
+        one host thread enqueue their barriers first and close afterwards)."""
         if self.handle:
+            if barrier:
+                self.lib.feo_comm_barrier(self.handle)
             self.ctx.sync()
             self.lib.feo_comm_destroy(self.handle)
             self.handle = None
@@ -133,7 +139,11 @@ class PeerBuffer:
             raise ValueError("the buffer is smaller than the tensor")
         return Tensor._wrap(shp, DeviceStorage(self.ctx, shp.size(), dtype, ptr=self.ptrs[self.rank], owner=self))
 
-    def close(self):
+    def close(self, comm=None):
+        """Every rank closes its buffer only once NO rank can still be reading it: pass the PeerComm (a barrier kernel runs
+        first), or put a host-side barrier (dist.barrier after a sync) in front of this call."""
+        if comm is not None and comm.handle:
+            self.lib.feo_comm_barrier(comm.handle)
         self.ctx.sync()
         for q in self._opened:
             self.lib.feo_peer_close(self.ctx.handle, C.c_void_p(q))

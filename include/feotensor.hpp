@@ -64,6 +64,7 @@ public:
         if (rc == FEO_OK) return;
         const std::string msg = feo_last_error(raw_);
         if (rc == FEO_ERR_SHAPE) throw ShapeError(msg);
+        if (rc == FEO_ERR_ARITH) throw Panic(msg);  // integer x/0 or MIN/-1: the reference panics (here: at the next sync point)
         throw BackendError(msg);
     }
     void sync() const { check(feo_sync(raw_)); }

@@ -44,7 +44,8 @@ typedef enum {
     FEO_ERR_SHAPE = 1,       /* ShapeError (error.rs:3-20) or a reference panic precondition */
     FEO_ERR_CUDA = 2,        /* CUDA runtime / driver failure, or no device */
     FEO_ERR_UNSUPPORTED = 3, /* dtype / algorithm / rank not supported by this build */
-    FEO_ERR_ARITH = 4        /* reserved: integer /0 or MIN/-1 is reported through feo_arith_flag */
+    FEO_ERR_ARITH = 4        /* integer x/0 or MIN/-1 (the reference panics): returned at once for a zero scalar divisor, else by
+                                the next feo_sync / feo_download after the kernel that met it (which wrote 0 there) */
 } feo_status;
 
 /* Element types: any `T: Num + PartialOrd + Copy` primitive the reference admits (tensor.rs:21). */
@@ -126,7 +127,8 @@ FEO_API int feo_fill_uniform(feo_ctx *ctx, int dtype, void *out, size_t n, uint6
 /* Add/Sub/Mul/Div<Tensor<T>> for Tensor<T> (tensor.rs:362-373, 405-416, 435-446, 478-489):
  * out[i] = a[i] op b[i], i < n.  The caller has checked shape equality (the reference asserts). */
 FEO_API int feo_ewise(feo_ctx *ctx, int op, int dtype, void *out, const void *a, const void *b, size_t n);
-/* Add/Sub/Mul/Div<T> for Tensor<T> (tensor.rs:336-359, 392-402, 465-475): out[i] = a[i] op *scalar. */
+/* Add/Sub/Mul/Div<T> for Tensor<T> (tensor.rs:336-359, 392-402, 465-475): out[i] = a[i] op *scalar.
+ * Integer division by a zero scalar returns FEO_ERR_ARITH without launching anything. */
 FEO_API int feo_ewise_scalar(feo_ctx *ctx, int op, int dtype, void *out, const void *a, const void *scalar_host, size_t n);
 /* Tensor::pow (tensor.rs:325-333), floats only: out[i] = a[i].powf(*power).  Exponents 2, 1, 0.5, 0, -1 use the
  * correctly rounded multiply / sqrt / divide (what a correctly rounded powf returns); other exponents use CUDA's
@@ -138,7 +140,9 @@ FEO_API int feo_pow(feo_ctx *ctx, int dtype, void *out, const void *a, const voi
 FEO_API int feo_ewise_broadcast(feo_ctx *ctx, int op, int dtype, void *out, const void *a, const void *b, int rank,
                         const size_t *shape, const size_t *a_strides, const size_t *b_strides);
 /* Sticky per-context flag set when an integer kernel met x/0 or MIN/-1 (the reference panics; the
- * kernel writes 0 there).  *flag receives it; clear != 0 resets it.  Synchronises the stream. */
+ * kernel writes 0 there).  *flag receives it; clear != 0 resets it.  Synchronises the stream.
+ * feo_sync and feo_download read (and clear) the same flag and return FEO_ERR_ARITH when it was set, so a
+ * host that only ever synchronises through them sees the reference's panic at its next look at the results. */
 FEO_API int feo_arith_flag(feo_ctx *ctx, int *flag, int clear);
 
 /* ---- reductions ------------------------------------------------------------------------------- */
@@ -203,6 +207,12 @@ FEO_API int feo_comm_create(feo_ctx *ctx, int rank, int world, void *const *wind
 FEO_API int feo_comm_destroy(feo_comm *comm);
 /* Where this rank's partial for the NEXT exchange goes (inside its own window) and its capacity. */
 FEO_API int feo_comm_slot(feo_comm *comm, void **dptr, size_t *bytes);
+/* Device-side waits for a peer (exchange flags, the sharded matmul's k-block flags) are bounded by ONE per-context
+ * timeout: environment variable FEO_PEER_TIMEOUT_S or feo_tune(ctx, 10, seconds); default 600 s, 0 = wait for ever.
+ * A wait that expires does not trap: the kernel raises a sticky status flag and goes on, the context stays usable.
+ * feo_peer_status synchronises the stream, stores the flag in *timed_out, clears it if asked, and returns FEO_ERR_CUDA
+ * (with a message) when it was set -- the results of that exchange are invalid. */
+FEO_API int feo_peer_status(feo_ctx *ctx, int *timed_out, int clear);
 /* Stream-ordered barrier across the ranks (no data). */
 FEO_API int feo_comm_barrier(feo_comm *comm);
 /* Combines the `world` partials sitting in the current slots: SUM / MAX / MIN; MEAN = sum then

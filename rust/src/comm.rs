@@ -10,19 +10,19 @@ use crate::device_tensor::DeviceTensor;
 use crate::ffi;
 use feotensor::{Axes, Shape};
 use std::os::raw::{c_int, c_void};
-use std::sync::Arc;
+use std::rc::Rc;
 
 pub type PeerHandle = [u8; ffi::FEO_PEER_HANDLE_BYTES];
 
 /// Peer-mappable device memory owned by this rank (zero-filled, freed on drop).
 pub struct PeerWindow {
-    ctx: Arc<Context>,
+    ctx: Rc<Context>,
     ptr: *mut c_void,
     bytes: usize,
 }
 
 impl PeerWindow {
-    pub fn new(ctx: &Arc<Context>, bytes: usize) -> PeerWindow {
+    pub fn new(ctx: &Rc<Context>, bytes: usize) -> PeerWindow {
         let mut ptr = std::ptr::null_mut();
         ctx.check(unsafe { ffi::feo_peer_alloc(ctx.raw, bytes, &mut ptr) });
         PeerWindow { ctx: ctx.clone(), ptr, bytes }
@@ -44,7 +44,7 @@ impl Drop for PeerWindow {
 /// The `world` windows of one node as seen from this rank, and the exchange kernels over them.
 /// Every rank must issue the same sequence of calls, like any collective.
 pub struct PeerComm {
-    ctx: Arc<Context>,
+    ctx: Rc<Context>,
     raw: *mut ffi::feo_comm,
     own: PeerWindow,
     opened: Vec<*mut c_void>,
@@ -55,7 +55,7 @@ pub struct PeerComm {
 impl PeerComm {
     /// `handles[r]` = rank r's `PeerWindow::export()`; `own` is this rank's window (its handle sits at `handles[rank]`).
     /// The caller synchronises the ranks (all windows created and mapped) before the first collective call.
-    pub fn new(ctx: &Arc<Context>, rank: usize, own: PeerWindow, handles: &[PeerHandle]) -> PeerComm {
+    pub fn new(ctx: &Rc<Context>, rank: usize, own: PeerWindow, handles: &[PeerHandle]) -> PeerComm {
         let world = handles.len();
         let mut windows: Vec<*mut c_void> = Vec::with_capacity(world);
         let mut opened = Vec::new();

@@ -6,7 +6,7 @@ use feotensor::error::ShapeError;
 use feotensor::shape::Shape;
 use std::marker::PhantomData;
 use std::os::raw::{c_int, c_void};
-use std::sync::Arc;
+use std::rc::Rc;
 
 /// Element types the backend knows (tensor.rs:21 admits any `Num + PartialOrd + Copy` primitive).
 pub unsafe trait DeviceElem: num::Num + PartialOrd + Copy {
@@ -24,21 +24,21 @@ pub(crate) fn dims_of(shape: &Shape) -> Vec<usize> {
 
 /// Dense row-major device buffer; indexing is `DynamicStorage::flatten` (storage.rs:18-38).
 pub struct DeviceStorage<T: DeviceElem> {
-    pub(crate) ctx: Arc<Context>,
+    pub(crate) ctx: Rc<Context>,
     pub(crate) ptr: *mut c_void,
     len: usize,
     _t: PhantomData<T>,
 }
 
 impl<T: DeviceElem> DeviceStorage<T> {
-    pub(crate) fn uninit(ctx: &Arc<Context>, len: usize) -> Self {
+    pub(crate) fn uninit(ctx: &Rc<Context>, len: usize) -> Self {
         let mut ptr = std::ptr::null_mut();
         ctx.check(unsafe { ffi::feo_malloc(ctx.raw, len * std::mem::size_of::<T>(), &mut ptr) });
         DeviceStorage { ctx: ctx.clone(), ptr, len, _t: PhantomData }
     }
 
     /// `DynamicStorage::new(data)` (storage.rs:13-15): copies the host data to the device.
-    pub fn new(ctx: &Arc<Context>, data: Vec<T>) -> Self {
+    pub fn new(ctx: &Rc<Context>, data: Vec<T>) -> Self {
         let s = Self::uninit(ctx, data.len());
         ctx.check(unsafe { ffi::feo_upload(ctx.raw, s.ptr, data.as_ptr().cast(), data.len() * std::mem::size_of::<T>()) });
         ctx.sync(); // `data` is dropped on return: the pageable copy must have left it

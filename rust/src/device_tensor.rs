@@ -28,7 +28,7 @@ impl<T: DeviceElem> DeviceTensor<T> {
         Ok(DeviceTensor { data: DeviceStorage::new(&Context::current(), data.to_vec()), shape: shape.clone() })
     }
 
-    pub(crate) fn uninit(ctx: &std::sync::Arc<Context>, shape: &Shape) -> DeviceTensor<T> {
+    pub(crate) fn uninit(ctx: &std::rc::Rc<Context>, shape: &Shape) -> DeviceTensor<T> {
         DeviceTensor { data: DeviceStorage::uninit(ctx, shape.size()), shape: shape.clone() }
     }
 

@@ -18,6 +18,7 @@ pub const FEO_OK: c_int = 0;
 pub const FEO_ERR_SHAPE: c_int = 1;
 pub const FEO_ERR_CUDA: c_int = 2;
 pub const FEO_ERR_UNSUPPORTED: c_int = 3;
+pub const FEO_ERR_ARITH: c_int = 4;
 
 pub const FEO_F32: c_int = 0;
 pub const FEO_F64: c_int = 1;
@@ -66,6 +67,8 @@ extern "C" {
     pub fn feo_vecmat(ctx: *mut feo_ctx, dtype: c_int, out: *mut c_void, v: *const c_void, a: *const c_void, k: usize, n: usize) -> c_int;
     pub fn feo_matmul(ctx: *mut feo_ctx, algo: c_int, dtype: c_int, c: *mut c_void, a: *const c_void, b: *const c_void, m: usize, k: usize, n: usize) -> c_int;
     pub fn feo_trim(ctx: *mut feo_ctx) -> c_int;
+    pub fn feo_arith_flag(ctx: *mut feo_ctx, flag: *mut c_int, clear: c_int) -> c_int;
+    pub fn feo_peer_status(ctx: *mut feo_ctx, timed_out: *mut c_int, clear: c_int) -> c_int;
 
     // Cross-GPU epilogues over peer memory (one process per GPU; the handles travel through the host's own rendezvous).
     pub fn feo_peer_alloc(ctx: *mut feo_ctx, bytes: usize, dptr: *mut *mut c_void) -> c_int;

@@ -122,8 +122,10 @@ def main():
             np.testing.assert_allclose(got[0], o.dot(p, q), rtol=1e-3 if dt == "f32" else 1e-11, atol=1e-3 if dt == "f32" else 1e-10)
         checks += 1
     launches = sum(c.launch_count() for c in ctxs)
+    for e in engines:  # one host thread drives every rank: enqueue all the closing barriers first, then tear down
+        e.comm.barrier()
     for e in engines:
-        e.comm.close()
+        e.comm.close(barrier=False)
     print(f"peer_loopback ok: world={world}, {checks} checks, {launches} kernel launches")
 
 

@@ -103,6 +103,20 @@ def run_checks(feo, sharded, o, dist, ctx, eng, rank, world, label, with_gather=
                     np.testing.assert_allclose(g, want, err_msg=msg, **tol)
                     np.testing.assert_allclose(g, single, err_msg=msg, **tol)
                 checks += 1
+        if dt in ("f32", "f64"):
+            # slices that are entirely -inf / +inf across every rank: the exchange's max / min must return the reference's
+            # values (seeded with the infinities, not with +-FLT_MAX)
+            xi = x.copy()
+            xi[:, 3, :] = -np.inf
+            xi[:, 5, 7] = np.inf
+            sxi = sharded.shard_rows(eng, xi)
+            for axes in ([0], [0, 2], [0, 1, 2], [1]):
+                for kind in ("max", "min"):
+                    got = sxi.reduce(kind, axes)
+                    g = got.local.to_numpy() if isinstance(got, sharded.ShardedTensor) else got.to_numpy()
+                    w = o.reduce(kind, xi, axes)
+                    np.testing.assert_array_equal(g, rows(w) if isinstance(got, sharded.ShardedTensor) else w, err_msg=f"{label} {dt} {kind} {axes} inf")
+                    checks += 1
         # Tensor::prod (tensor.rs:311-322) with the left operand split and the right one replicated: no exchange, one IEEE
         # multiply per element -> bit-exact for every dtype
         u, v = gen(dt, (R * 6,)), gen(dt, (77,))

@@ -220,12 +220,26 @@ def test_elementwise_special_values_and_wrap(feo, oracle):
     np.testing.assert_array_equal((ti + tj).to_numpy(), oracle.ewise("add", ia, ib))
     np.testing.assert_array_equal((ti * tj).to_numpy(), oracle.ewise("mul", ia, ib))
     np.testing.assert_array_equal((ti / np.int32(2)).to_numpy(), oracle.ewise_scalar("div", ia, 2))  # truncation toward zero
-    # x/0 and MIN/-1: the reference panics; the kernel writes 0 and raises the sticky flag
+    # x/0 and MIN/-1: the reference panics at the operator; the kernel writes 0, raises the sticky flag, and the next
+    # synchronisation point (download / sync) reports it as FEO_ERR_ARITH -> ReferencePanic, clearing the flag
     ctx = feo.Context.default()
     assert ctx.arith_flag() == 0
-    r = (ti / feo.Tensor(feo.shape(4), np.array([1, -1, 0, 1], np.int32))).to_numpy()
-    assert ctx.arith_flag() == 1 and ctx.arith_flag() == 0
-    np.testing.assert_array_equal(r, np.array([2 ** 31 - 1, 0, 0, -7], np.int32))
+    q = ti / feo.Tensor(feo.shape(4), np.array([1, -1, 0, 1], np.int32))
+    with pytest.raises(feo.ReferencePanic):
+        q.to_numpy()
+    assert ctx.arith_flag() == 0  # cleared by the report
+    np.testing.assert_array_equal(q.to_numpy(), np.array([2 ** 31 - 1, 0, 0, -7], np.int32))
+    q = ti / feo.Tensor(feo.shape(4), np.array([1, 1, 0, 1], np.int32))
+    assert ctx.arith_flag(clear=False) == 1  # the explicit poll sees it too
+    with pytest.raises(feo.ReferencePanic):
+        ctx.sync()
+    ctx.sync()
+    # a zero integer scalar divisor is rejected on the host, nothing is launched (tensor.rs:465-475 panics at element 0)
+    for dt_ in (np.int32, np.int64, np.uint32):
+        with pytest.raises(feo.ReferencePanic):
+            feo.Tensor(feo.shape(3), np.array([1, 2, 3], dt_)) / dt_(0)
+    assert np.isinf((feo.Tensor(feo.shape(2), np.array([1.0, -1.0], np.float32)) / np.float32(0)).to_numpy()).all()  # floats: IEEE
+    feo.Tensor(feo.shape(4), np.arange(4, dtype=np.int32)).mean([0]).to_numpy()  # an ordinary integer mean raises nothing
     # i64: operands inside the i32 range take a 32-bit division, everything else the 64-bit one -- same quotients either way
     la = np.array([7, -7, 2 ** 31 - 1, -2 ** 31, -2 ** 31, 2 ** 31, -2 ** 31 - 1, 2 ** 62, -2 ** 63, -2 ** 63, 10 ** 15, -10 ** 15, 5, 0],
                   np.int64)
@@ -233,8 +247,9 @@ def test_elementwise_special_values_and_wrap(feo, oracle):
     tl, tm = feo.Tensor(feo.shape(la.size), la), feo.Tensor(feo.shape(lb.size), lb)
     np.testing.assert_array_equal((tl / tm).to_numpy(), oracle.ewise("div", la, lb))
     assert ctx.arith_flag() == 0
-    r = (tl / feo.Tensor(feo.shape(la.size), np.array([1, 0, 1, 1, 1, 1, 1, 1, -1, 1, 1, 1, 1, 1], np.int64))).to_numpy()
+    q = tl / feo.Tensor(feo.shape(la.size), np.array([1, 0, 1, 1, 1, 1, 1, 1, -1, 1, 1, 1, 1, 1], np.int64))
     assert ctx.arith_flag() == 1 and ctx.arith_flag() == 0
+    r = q.to_numpy()
     assert r[1] == 0 and r[8] == 0 and r[0] == 7 and r[7] == 2 ** 62
 
 
@@ -280,7 +295,7 @@ BCAST_CASES = [
 ]
 
 
-@pytest.mark.parametrize("dt", ["f32", "f64", "i32", "i64"])
+@pytest.mark.parametrize("dt", ALL)
 def test_broadcast_bit_exact(feo, oracle, dt):
     rng = np.random.default_rng(200)
     for sa, sb in BCAST_CASES:
@@ -384,6 +399,73 @@ def test_reductions_vs_oracle(feo, oracle, dt):
                 bound = 8 * gamma(n + 2, dt) * scale + 1e-300
                 assert np.all(np.abs(g.reshape(-1).astype(np.float64) - exact) <= bound), msg
                 assert np.all(np.abs(want.reshape(-1).astype(np.float64) - exact) <= bound), msg + " (oracle)"
+
+
+NONFINITE_CASES = [((6, 40), [1]), ((6, 40), [0]), ((6, 40), []), ((3, 5, 64), [0, 2]), ((300, 3), [1]), ((2, 5000), [1]),
+                   ((64, 128, 256), [0, 2]), ((64, 128, 256), [0]), ((4, 70000), [1]), ((9, 31), [1]), ((5000, 6), [0])]
+
+
+def _one_target_slice(shape, axes):
+    """Index tuple selecting every element that reduces into ONE output (the first target), for `axes` removed."""
+    if not axes:
+        return tuple(slice(None) for _ in shape)
+    return tuple(slice(None) if d in axes else min(1, shape[d] - 1) for d in range(len(shape)))
+
+
+@pytest.mark.parametrize("dt", FLOATS)
+def test_max_min_with_infinities_match_the_reference(feo, oracle, dt):
+    """Slices that are entirely -inf / +inf, and stray infinities elsewhere: no NaN is involved, so the reference's init
+    fold (tensor.rs:234-237) is well defined and the GPU must return the oracle's values bit for bit -- a -FLT_MAX / +FLT_MAX
+    seed would not.  Both the scalar path (axes == []) and the axis path, small and split geometries."""
+    rng = np.random.default_rng(310)
+    for shape, axes in NONFINITE_CASES:
+        for fill in (-np.inf, np.inf):
+            x = rand(oracle, rng, dt, shape)
+            x[_one_target_slice(shape, axes)] = fill
+            flat = x.reshape(-1)
+            flat[rng.integers(0, flat.size, 5)] = -fill     # stray opposite infinities
+            t = feo.Tensor(feo.Shape(shape), x)
+            for kind in ("max", "min"):
+                got, want = getattr(t, kind)(axes).to_numpy(), oracle.reduce(kind, x, axes)
+                np.testing.assert_array_equal(got, want, err_msg=f"{dt} {kind} {shape} {axes} fill {fill}")
+            s = t.sum(axes).to_numpy()
+            assert np.array_equal(np.isfinite(s), np.isfinite(oracle.reduce("sum", x, axes))), f"{dt} sum {shape} {axes}"
+
+
+@pytest.mark.parametrize("dt", FLOATS)
+def test_nan_inputs_neither_crash_nor_poison_other_outputs(feo, oracle, dt):
+    """NaN ordering is unspecified by SURVEY 8a-quirks (the reference's result depends on WHERE in the whole tensor the NaN
+    sits).  What the GPU path guarantees, and this pins: a NaN never wins max / min (the reference's strict compares skip
+    it too, tensor.rs:248), an all-NaN slice yields the seed (-inf / +inf), a NaN reaches only the sum / mean / var outputs
+    it belongs to, and every output whose slice holds no NaN is exactly what it is without the NaN anywhere."""
+    rng = np.random.default_rng(311)
+    for shape, axes in NONFINITE_CASES:
+        x = rand(oracle, rng, dt, shape)
+        clean = feo.Tensor(feo.Shape(shape), x)
+        y = x.copy()
+        y[_one_target_slice(shape, axes)] = np.nan                     # one output's whole slice
+        flat = y.reshape(-1)
+        flat[rng.integers(0, flat.size, 7)] = np.nan                   # and a few in the middle of others
+        t = feo.Tensor(feo.Shape(shape), y)
+        ax = tuple(axes) if axes else None
+        has_nan = np.atleast_1d(np.isnan(y).any(axis=ax))
+        all_nan = np.atleast_1d(np.isnan(y).all(axis=ax))
+        for kind, npf, seed in (("max", np.fmax, -np.inf), ("min", np.fmin, np.inf)):
+            got = getattr(t, kind)(axes).to_numpy().reshape(-1)
+            want = np.atleast_1d(npf.reduce(y, axis=ax) if ax is not None else npf.reduce(y.reshape(-1))).reshape(-1).copy()
+            want[all_nan.reshape(-1)] = seed
+            np.testing.assert_array_equal(got, want, err_msg=f"{dt} {kind} {shape} {axes}")
+        for kind in ("sum", "mean", "var"):
+            got = getattr(t, kind)(axes).to_numpy().reshape(-1)
+            ref = getattr(clean, kind)(axes).to_numpy().reshape(-1)
+            assert np.array_equal(np.isnan(got), has_nan.reshape(-1)), f"{dt} {kind} {shape} {axes}: NaN reached the wrong outputs"
+            keep = ~has_nan.reshape(-1)
+            np.testing.assert_array_equal(got[keep], ref[keep], err_msg=f"{dt} {kind} {shape} {axes}: clean outputs changed")
+        # signed zeros: compared by value (which zero wins a tie is unspecified)
+        z = np.zeros(shape, npdt(oracle, dt))
+        z.reshape(-1)[::2] = -0.0
+        tz = feo.Tensor(feo.Shape(shape), z)
+        assert np.all(tz.max(axes).to_numpy() == 0) and np.all(tz.min(axes).to_numpy() == 0) and np.all(tz.sum(axes).to_numpy() == 0)
 
 
 def test_reduction_split_counts_agree(feo, oracle):
