@@ -38,6 +38,15 @@ SLAB_BYTES = 4 * (SLAB_ROWS * D + D * D + SLAB_ROWS * D * D)   # algorithmic byt
 SEED = 0xFE07E450
 
 
+def bench_config(world):
+    """`config` of the JSON line -- the same dict for the B200 arm and for --impl reference."""
+    return {"workload": "C2 broadcast mul a[4096,1,4096]*b[1,4096,4096] f32 in out[16,4096,4096] slabs",
+            "rows_per_gpu": ROWS_PER_RANK, "slabs_per_step_per_gpu": ROWS_PER_RANK // SLAB_ROWS,
+            "parallelism": f"leading-axis shard x{world}, no collective",
+            "l2": "32 GiB written per step per GPU >> 126 MB L2 (b, 64 MiB, is meant to stay L2-resident)",
+            "algorithmic_bytes_per_launch": SLAB_BYTES}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -97,19 +106,133 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_slab(oracle, np, n_slabs):
+class SuiteClocks:
+    """One nvidia-smi sampler (50 ms period, time-stamped) across the whole suite; `mark(name)` brackets an entry's timed
+    region on the host clock and `finish()` hands every entry the SM clock / throttle reasons sampled inside its bracket
+    (or, for entries shorter than the sampling period, the nearest sample)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.path, self.marks = device, None, None, {}
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-f", self.path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    class _Mark:
+        def __init__(self, owner, name):
+            self.owner, self.name = owner, name
+
+        def __enter__(self):
+            self.t0 = time.time()
+
+        def __exit__(self, *exc):
+            self.owner.marks[self.name] = (self.t0, time.time())
+
+    def mark(self, name):
+        return SuiteClocks._Mark(self, name)
+
+    def finish(self):
+        from datetime import datetime
+        out = {}
+        if not self.proc:
+            return out
+        time.sleep(0.1)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = []
+            for r in open(self.path).read().strip().split("\n"):
+                f = [c.strip() for c in r.split(",")]
+                if len(f) < 8:
+                    continue
+                rows.append((datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp(), float(f[1]), float(f[2]), float(f[3]),
+                             [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8])
+                              if v.lower().startswith("active")]))
+            for name, (t0, t1) in self.marks.items():
+                inside = [r for r in rows if t0 - 0.05 <= r[0] <= t1 + 0.05]
+                if not inside and rows:
+                    inside = [min(rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))]
+                if inside:
+                    out[name] = {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": inside[0][2], "samples": len(inside),
+                                 "power_w_max": max(r[3] for r in inside), "reasons": sorted({x for r in inside for x in r[4]})}
+        except Exception as e:
+            out["error"] = str(e)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        return out
+
+
+def sample_bytes(rows):
+    """Algorithmic bytes of a `rows`-row piece of the workload: out[rows,4096,4096] = a[rows,1,4096] * b."""
+    return 4 * (rows * D + D * D + rows * D * D)
+
+
+def cpu_reference_slab(oracle, np, n_slabs, rows=SLAB_ROWS):
     """The reference's CPU path for one workload sample: the reference has no broadcasting
     (tensor.rs:439 asserts equal shapes), so the operands are materialised to the slab shape and then
-    multiplied by the reference's Mul (zero-fill + copy + indexed loop, tensor.rs:435-446)."""
-    a = oracle.fill_uniform("f32", SLAB_ROWS * D, SEED + 2, 0, -1.0, 1.0).reshape(SLAB_ROWS, 1, D)
+    multiplied by the reference's Mul (zero-fill + copy + indexed loop, tensor.rs:435-446).
+    `rows` < 16 takes the leading rows of a slab (a bounded sample of the same work)."""
+    a = oracle.fill_uniform("f32", rows * D, SEED + 2, 0, -1.0, 1.0).reshape(rows, 1, D)
     b = oracle.fill_uniform("f32", D * D, SEED + 3, 0, -1.0, 1.0).reshape(1, D, D)
     t0 = time.perf_counter()
     for _ in range(n_slabs):
-        am = oracle.materialize(a, (SLAB_ROWS, D, D))
-        bm = oracle.materialize(b, (SLAB_ROWS, D, D))
+        am = oracle.materialize(a, (rows, D, D))
+        bm = oracle.materialize(b, (rows, D, D))
         out = oracle.ewise("mul", am, bm, faithful=True)
     dt = time.perf_counter() - t0
-    return dt, float(out[3, 5, 7])
+    return dt, float(out[rows - 1, 5, 7])
+
+
+def cpu_other_configs(oracle, np):
+    """CPU baselines for the other BASELINE configs, one host core, bounded samples:
+    structure-faithful matmul (matrix.rs:80-88: two coordinate allocations and two flatten calls per multiply-add) at
+    N = 256 and 512, extrapolated with N^3 to 8192; the same-order port of sum / var / max over the leading axis on a
+    [128,16384,8] slice of config 3; the same-order dot on 1e8 elements and outer product 1024 x 65536 of config 5."""
+    out = {}
+
+    def sec(fn):
+        t0 = time.perf_counter()
+        fn()
+        return time.perf_counter() - t0
+    for n in (256, 512):
+        A = oracle.fill_uniform("f32", n * n, SEED + 40).reshape(n, n)
+        B = oracle.fill_uniform("f32", n * n, SEED + 41).reshape(n, n)
+        tf, tp = sec(lambda: oracle.matmul(A, B, faithful=True)), sec(lambda: oracle.matmul(A, B))
+        out[f"C4_matmul_{n}"] = {"faithful_s": round(tf, 4), "port_s": round(tp, 4), "faithful_GFLOP/s": round(2.0 * n ** 3 / tf / 1e9, 3),
+                                 "port_GFLOP/s": round(2.0 * n ** 3 / tp / 1e9, 3)}
+    t512 = out["C4_matmul_512"]
+    out["C4_matmul_8192_extrapolated"] = {"faithful_s": round(t512["faithful_s"] * 16 ** 3, 1), "port_s": round(t512["port_s"] * 16 ** 3, 1),
+                                          "note": "N = 512 time x 16^3 (flagged: extrapolated, B no longer fits the CPU caches at 8192)"}
+    x = oracle.fill_uniform("f32", 128 * 16384 * 8, SEED + 30).reshape(128, 16384, 8)
+    for kind in ("sum", "var", "max"):
+        t = sec(lambda: oracle.reduce(kind, x, [0]))
+        out[f"C3_{kind}_axes0_port"] = {"s": round(t, 4), "GB/s": round(4.0 * (x.size + 16384 * 8) / t / 1e9, 3), "sample": "[128,16384,8] of [16384,16384,8]"}
+    xs = x[:8]
+    t = sec(lambda: oracle.reduce("sum", np.ascontiguousarray(xs), [0], faithful=True))
+    out["C3_sum_axes0_faithful"] = {"s": round(t, 4), "GB/s": round(4.0 * (xs.size + 16384 * 8) / t / 1e9, 4), "sample": "[8,16384,8]",
+                                    "note": "per-element coordinate vectors and flatten calls like tensor.rs:94-105"}
+    p_, q_ = oracle.fill_uniform("f32", 10 ** 8, SEED + 52), oracle.fill_uniform("f32", 10 ** 8, SEED + 53)
+    t = sec(lambda: oracle.dot(p_, q_))
+    out["C5_dot_port"] = {"s": round(t, 4), "GB/s": round(8e8 / t / 1e9, 3), "sample": "1e8 of 1e9 elements"}
+    u, v = oracle.fill_uniform("f32", 1024, SEED + 50), oracle.fill_uniform("f32", 65536, SEED + 51)
+    t = sec(lambda: oracle.prod(u, v))
+    out["C5_outer_port"] = {"s": round(t, 4), "GB/s": round(4.0 * (1024 + 65536 + 1024 * 65536) / t / 1e9, 3), "sample": "1024 x 65536 of 65536 x 65536"}
+    out["cores"] = 1
+    return out
 
 
 def cpu_config1(oracle, np):
@@ -136,9 +259,11 @@ def cpu_config1(oracle, np):
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the Rust crate cannot be built in
-    this image) through its stock code path: single-threaded, one 1 GiB slab per step.  Because slabs are independent
-    tensors a host program could drive the reference from several threads itself; that figure is reported beside it
-    (`all_threads`, at most 8 threads of 3 GiB each) -- or as the headline with --ref-threads N."""
+    this image) through its stock code path, single-threaded like the reference.  Honours --steps / --warmup: every step
+    is a bounded sample of the workload -- the leading `rows` rows of one out[16,4096,4096] slab, `rows` chosen from a
+    calibration row so that the whole run stays inside a wall budget (a full slab per step when that fits).  Slabs are
+    independent tensors, so a host program could drive the reference from several threads itself; that figure is
+    reported beside it (`all_threads`) -- or as the headline with --ref-threads N."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -147,35 +272,39 @@ def run_reference(args):
     import numpy as np
     from oracle import feo_oracle as oracle
     oracle.lib()
-    if args.warmup > 0:
-        cpu_reference_slab(oracle, np, 1)
-    steps = max(1, min(args.steps, 4))
-
-    def run(threads):
-        t0 = time.perf_counter()
-        if threads == 1:
-            cpu_reference_slab(oracle, np, steps)
-        else:
-            with ThreadPoolExecutor(max_workers=threads) as pool:  # the C calls release the GIL
-                list(pool.map(lambda _: cpu_reference_slab(oracle, np, steps), range(threads)))
-        dt = time.perf_counter() - t0
-        return dt, threads * steps * SLAB_BYTES / dt / 1e9
+    K, W = max(args.steps, 1), max(args.warmup, 0)
     threads = max(1, args.ref_threads)
-    dt, val = run(threads)
+    t_row, _ = cpu_reference_slab(oracle, np, 1, rows=1)          # calibration (also pages the library in)
+    budget_s = float(os.environ.get("FEO_REF_BUDGET_S", "100"))
+    rows = int(max(1, min(SLAB_ROWS, budget_s / ((K + W) * max(t_row, 1e-3)))))
+
+    def run(nthreads, steps):
+        t0 = time.perf_counter()
+        if nthreads == 1:
+            cpu_reference_slab(oracle, np, steps, rows)
+        else:
+            with ThreadPoolExecutor(max_workers=nthreads) as pool:  # the C calls release the GIL
+                list(pool.map(lambda _: cpu_reference_slab(oracle, np, steps, rows), range(nthreads)))
+        dt = time.perf_counter() - t0
+        return dt, nthreads * steps * sample_bytes(rows) / dt / 1e9
+    if W:
+        run(threads, W)
+    dt, val = run(threads, K)
     many = max(1, min(os.cpu_count() or 1, 8))
     extra = None
     if threads == 1 and many > 1:
-        _, v_many = run(many)
-        extra = {"threads": many, "value": v_many, "unit": UNIT, "note": "one independent slab per host thread"}
+        _, v_many = run(many, max(1, min(K, 3)))
+        extra = {"threads": many, "value": v_many, "unit": UNIT, "note": "one independent sample per host thread"}
+    sample = (f"{K} steps (+{W} warm-up) x {threads} thread(s); a step = the leading {rows} row(s) of one out[16,4096,4096] slab: materialise "
+              f"a and b, then the reference Mul (tensor.rs:435-446); {sample_bytes(rows)} algorithmic bytes per step")
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2 broadcast mul a[4096,1,4096]*b[1,4096,4096] f32, one out[16,4096,4096] slab per thread per step",
-                   "note": "reference semantics: materialise both operands, then Tensor*Tensor (tensor.rs:435-446)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{steps} steps x {threads} thread(s), one out[16,4096,4096] slab each",
-                         "host_cores_available": os.cpu_count(), "all_threads": extra},
+        "config": bench_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "rows_per_step": rows,
+                         "host_cores_available": os.cpu_count(), "all_threads": extra,
+                         "note": "reference semantics: the reference cannot broadcast, so both operands are materialised first"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -196,11 +325,27 @@ def timed(torch, fn, iters, warmup=1):
     return e0.elapsed_time(e1) / iters  # ms
 
 
-def run_suite(torch, feo, L, ctx, hbm_peak, tf_peak):
+def run_suite(torch, feo, L, ctx, hbm_peak, tf_peak, device=0):
     """The other BASELINE configs at N = 1 (each value measured with CUDA events after warm-up; inputs are
-    far larger than L2 except config 1, which is flagged)."""
+    far larger than L2 except config 1, which is flagged).  Every entry carries the SM clock / throttle reasons sampled
+    while it was being timed (`clocks`)."""
     vp = C.c_void_p
     suite = {}
+    sampler = SuiteClocks(device).start()
+    _timed = globals()["timed"]
+    seq = [0]
+
+    def timed(torch_, fn, iters, warmup=1):   # shadows the module-level helper: same timing, bracketed for the clock sampler
+        seq[0] += 1
+        with sampler.mark(seq[0]):
+            return _timed(torch_, fn, iters, warmup)
+
+    class _Tracked(dict):  # remembers which timed() call (the latest one) produced each entry
+        def __setitem__(self, k, v):
+            if isinstance(v, dict):
+                v.setdefault("_mark", seq[0])
+            dict.__setitem__(self, k, v)
+    suite = _Tracked()
 
     def dev(nbytes):
         return torch.empty(nbytes, dtype=torch.uint8, device="cuda")
@@ -316,7 +461,12 @@ def run_suite(torch, feo, L, ctx, hbm_peak, tf_peak):
         suite[f"C4_matmul_{algo}"] = entry
     del A, B, Cm
     torch.cuda.empty_cache()
-    return suite
+    clocks = sampler.finish()
+    for entry in suite.values():
+        m = entry.pop("_mark", None)
+        if m in clocks:
+            entry["clocks"] = clocks[m]
+    return dict(suite)
 
 
 class Parity:
@@ -843,10 +993,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2 broadcast mul a[4096,1,4096]*b[1,4096,4096] f32 in out[16,4096,4096] slabs",
-                   "rows_per_gpu": ROWS_PER_RANK, "slabs_per_step_per_gpu": nslabs, "parallelism": f"leading-axis shard x{world}, no collective",
-                   "l2": "32 GiB written per step per GPU >> 126 MB L2 (b, 64 MiB, is meant to stay L2-resident)",
-                   "algorithmic_bytes_per_launch": SLAB_BYTES},
+        "config": bench_config(world),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "kernel": "bcast_tile_kernel<float,MUL,16B,8,4>", "launch_ms": launch_ms, "peak_source": peak_src},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 4 * (ROWS_PER_RANK * D + D * D),
@@ -859,7 +1006,7 @@ def main():
     torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_suite:
         try:
-            line["suite"] = run_suite(torch, feo, L, ctx, hbm_peak, tf_peak)
+            line["suite"] = run_suite(torch, feo, L, ctx, hbm_peak, tf_peak, local)
         except Exception as e:  # the headline line must still be printed
             line["suite"] = {"error": repr(e)}
     if world > 1 and not args.no_suite:
@@ -896,6 +1043,10 @@ def main():
             line["cpu_baseline"]["config1_ms"] = cpu_config1(oracle, np)
         except Exception as e:
             line["cpu_baseline"]["config1_ms"] = {"error": repr(e)}
+        try:
+            line["cpu_baseline"]["other_configs"] = cpu_other_configs(oracle, np)
+        except Exception as e:
+            line["cpu_baseline"]["other_configs"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

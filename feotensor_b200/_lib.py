@@ -32,7 +32,7 @@ _vp, _sz, _int = C.c_void_p, C.c_size_t, C.c_int
 _szp = C.POINTER(C.c_size_t)
 
 # name -> (restype, argtypes); must list every FEO_API symbol of include/feotensor_b200.h
-PEER_HANDLE_BYTES, MAX_PEERS = 64, 8
+PEER_HANDLE_BYTES, MAX_PEERS, NCCL_UNIQUE_ID_BYTES = 64, 8, 128
 
 SIGNATURES = {
     "feo_abi_version": (_int, []),
@@ -92,6 +92,17 @@ SIGNATURES = {
     "feo_comm_gather": (_int, [_vp, _vp, C.POINTER(_vp), _sz]),
     "feo_matmul_sharded_b": (_int, [_vp, _int, _int, _vp, _vp, C.POINTER(_vp), _sz, _sz, _sz]),
     "feo_dot_sharded": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _sz]),
+    "feo_nccl_unique_id": (_int, [C.c_char_p]),
+    "feo_nccl_comm_create": (_int, [_vp, C.c_char_p, _int, _int, C.POINTER(_vp)]),
+    "feo_nccl_comm_create_all": (_int, [C.POINTER(_vp), _int, C.POINTER(_vp)]),
+    "feo_nccl_comm_destroy": (_int, [_vp]),
+    "feo_nccl_group_start": (_int, []),
+    "feo_nccl_group_end": (_int, []),
+    "feo_nccl_allreduce": (_int, [_vp, _int, _int, _vp, _sz]),
+    "feo_nccl_allgather": (_int, [_vp, _vp, _vp, _sz]),
+    "feo_reduce_sharded_nccl": (_int, [_vp, _int, _int, _vp, _vp, _int, _szp, _int, _szp, _vp]),
+    "feo_dot_sharded_nccl": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _sz]),
+    "feo_matmul_sharded_b_nccl": (_int, [_vp, _int, _int, _vp, _vp, _vp, _sz, _sz, _sz]),
 }
 
 _lib = None

@@ -14,6 +14,10 @@ A ShardedTensor is one dense row-major block of leading rows per rank.  Which op
   dot                                                 all-reduce(SUM) of per-shard partial dots
   matmul (A row-sharded)                              none if B is replicated, else all-gather of B
 
+With an `NcclComm` attached (`CudaEngine(nccl=NcclComm(ctx))`) the same NCCL exchanges are issued by the library itself
+(`csrc/nccl_route.cu`: feo_reduce_sharded_nccl, feo_dot_sharded_nccl, feo_matmul_sharded_b_nccl) -- the route a host
+that is not Python takes; torch.distributed then only carries NCCL's 128-byte unique id at start-up.
+
 With a `PeerComm` attached to the engine (`CudaEngine(comm=PeerComm(...))`) the exchange steps above do not call
 NCCL: the local reduction writes its partial straight into a peer-mapped window and ONE kernel per rank signals, waits
 and combines the partials over NVLink in rank order with the epilogue (mean's division, var's Chan merge -- or, for
@@ -100,6 +104,33 @@ class PeerComm:
             self._opened, self._own = [], None
 
 
+class NcclComm:
+    """The library's own NCCL communicator (csrc/nccl_route.cu): the exchange steps as NCCL calls issued INSIDE the C ABI.
+
+    torch.distributed only carries the 128-byte unique id from rank 0 to the others at start-up -- any rendezvous a host
+    has would do; afterwards `feo_reduce_sharded_nccl` / `feo_dot_sharded_nccl` / `feo_matmul_sharded_b_nccl` are single
+    C calls a Rust or C++ host makes just the same."""
+
+    def __init__(self, ctx, rank=None, world=None, group=None):
+        dist = _dist()
+        self.ctx, self.lib = ctx, ctx.lib
+        self.rank = dist.get_rank(group) if rank is None else int(rank)
+        self.world = dist.get_world_size(group) if world is None else int(world)
+        uid = C.create_string_buffer(L.NCCL_UNIQUE_ID_BYTES)
+        if self.rank == 0:
+            ctx.check(self.lib.feo_nccl_unique_id(uid))
+        box = [bytes(uid.raw)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        h = C.c_void_p()
+        ctx.check(self.lib.feo_nccl_comm_create(ctx.handle, box[0], self.rank, self.world, C.byref(h)))
+        self.handle = h
+
+    def close(self):
+        if self.handle:
+            self.lib.feo_nccl_comm_destroy(self.handle)
+            self.handle = None
+
+
 class PeerBuffer:
     """One device allocation per rank that every rank can read: `ptrs[r]` is rank r's block as mapped in this process.
 
@@ -155,13 +186,14 @@ class PeerBuffer:
 class CudaEngine:
     """Local compute on this rank's GPU through libfeotensor_b200 (arrays are core.Tensor)."""
 
-    def __init__(self, ctx=None, comm=None):
+    def __init__(self, ctx=None, comm=None, nccl=None):
         import torch
 
         from .core import Context
         self.torch = torch
         self.ctx = ctx or Context.default()
         self.comm = comm  # PeerComm: exchanges run as native peer-memory kernels instead of NCCL calls
+        self.nccl = nccl  # NcclComm: exchanges are NCCL calls issued inside the C ABI (no torch.distributed on the data path)
         # one stream for the library and for torch's collectives, so NCCL is ordered after the kernels
         self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 
@@ -231,6 +263,30 @@ class CudaEngine:
         ctx.check(ctx.lib.feo_reduce_sharded(self.comm.handle, L.KIND_CODES[kind], x.data.code, C.c_void_p(out.data.ptr),
                                              C.c_void_p(x.data.ptr), len(dims), L.sizes(dims), len(local_axes), L.sizes(local_axes),
                                              d.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def reduce_sharded_nccl(self, kind, x, local_axes, nout, divisor):
+        """Local reduction + NCCL exchange + epilogue, all inside the C ABI (csrc/nccl_route.cu)."""
+        ctx, dims = self.ctx, self.dims(x)
+        out = self.empty([nout], x.dtype)
+        d = np.array([divisor], dtype=x.dtype)
+        ctx.check(ctx.lib.feo_reduce_sharded_nccl(self.nccl.handle, L.KIND_CODES[kind], x.data.code, C.c_void_p(out.data.ptr),
+                                                  C.c_void_p(x.data.ptr), len(dims), L.sizes(dims), len(local_axes), L.sizes(local_axes),
+                                                  d.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def dot_sharded_nccl(self, a, b):
+        ctx = self.ctx
+        out = self.empty([1], a.dtype)
+        ctx.check(ctx.lib.feo_dot_sharded_nccl(self.nccl.handle, a.data.code, C.c_void_p(out.data.ptr), C.c_void_p(a.data.ptr),
+                                               C.c_void_p(b.data.ptr), 1, a.size()))
+        return out
+
+    def matmul_sharded_b_nccl(self, A, B_local, K, N, algo="auto"):
+        ctx, M = self.ctx, self.dims(A)[0]
+        out = self.empty([M, N], A.dtype)
+        ctx.check(ctx.lib.feo_matmul_sharded_b_nccl(self.nccl.handle, L.ALGO_CODES[algo], A.data.code, C.c_void_p(out.data.ptr),
+                                                    C.c_void_p(A.data.ptr), C.c_void_p(B_local.data.ptr), M, K, N))
         return out
 
     def dot_sharded(self, a, b):
@@ -346,6 +402,9 @@ class ShardedTensor:
             if getattr(eng, "comm", None) is not None and peer is not None:
                 out_local = eng.matmul_sharded_b(self.local, peer.ptrs, B.global_dims[0], B.global_dims[1], algo)
                 return self._like(out_local, [self.global_dims[0], B.global_dims[1]])
+            if getattr(eng, "nccl", None) is not None:
+                out_local = eng.matmul_sharded_b_nccl(self.local, B.local, B.global_dims[0], B.global_dims[1], algo)
+                return self._like(out_local, [self.global_dims[0], B.global_dims[1]])
             mine = eng.as_torch(B.local)
             full = eng.empty(B.global_dims, eng.dtype(B.local))
             dist.all_gather(list(eng.as_torch(full).view(self.world, -1).unbind(0)), mine, group=self.group)
@@ -377,6 +436,8 @@ class ShardedTensor:
         if comm is not None and kind in ("sum", "mean", "var", "max", "min") and \
                 nout * dtype.itemsize * (2 if kind == "var" else 1) <= comm.slot_bytes:
             return eng.reshape(eng.reduce_sharded(kind, self.local, local_axes, nout, n_div), out_dims)
+        if getattr(eng, "nccl", None) is not None:
+            return eng.reshape(eng.reduce_sharded_nccl(kind, self.local, local_axes, nout, n_div), out_dims)
 
         def allreduce(t, op):
             if dtype == np.uint32 and op != "sum":  # order-preserving bias for the int32 view
@@ -411,6 +472,8 @@ class ShardedTensor:
             raise ValueError("assertion failed: self.shape() == rhs.shape()")
         if getattr(eng, "comm", None) is not None:
             return eng.dot_sharded(self.local, rhs.local)
+        if getattr(eng, "nccl", None) is not None:
+            return eng.dot_sharded_nccl(self.local, rhs.local)
         part = eng.dot(self.local, rhs.local)
         _dist().all_reduce(eng.as_torch(part), group=self.group)
         return part

@@ -238,6 +238,38 @@ FEO_API int feo_matmul_sharded_b(feo_comm *comm, int algo, int dtype, void *C, c
 /* DynamicVector::vecmul (vector.rs:71-78) on identically sharded operands [batch, n_local]. */
 FEO_API int feo_dot_sharded(feo_comm *comm, int dtype, void *out, const void *a, const void *b, size_t batch, size_t n_local);
 
+/* ---- the NCCL route (north star: NCCL allreduce after reductions, NCCL allgather of B) ------------- */
+/* The same exchanges through NCCL, inside the ABI, so a host that is not Python needs no torch.distributed: rank 0 calls
+ * feo_nccl_unique_id and moves the 128 bytes to the other ranks through its own rendezvous, every rank then calls
+ * feo_nccl_comm_create (ncclCommInitRank) -- or one process calls feo_nccl_comm_create_all over its G contexts
+ * (ncclCommInitAll, the process model of SURVEY 8e) and brackets calls on several communicators with
+ * feo_nccl_group_start / feo_nccl_group_end.  libnccl.so.2 is dlopen'ed on first use (FEO_NCCL_LIB overrides the
+ * name); without it these return FEO_ERR_UNSUPPORTED.  The peer-memory kernels above are the faster route at the
+ * BASELINE sizes; this is the portable one and the baseline they are measured against. */
+#define FEO_NCCL_UNIQUE_ID_BYTES 128
+typedef struct feo_nccl feo_nccl;
+FEO_API int feo_nccl_unique_id(unsigned char *id /* [FEO_NCCL_UNIQUE_ID_BYTES] */);
+FEO_API int feo_nccl_comm_create(feo_ctx *ctx, const unsigned char *id, int rank, int world, feo_nccl **comm);
+FEO_API int feo_nccl_comm_create_all(feo_ctx *const *ctxs, int ndev, feo_nccl **comms /* [ndev] */);
+FEO_API int feo_nccl_comm_destroy(feo_nccl *comm);
+FEO_API int feo_nccl_group_start(void);
+FEO_API int feo_nccl_group_end(void);
+/* In-place ncclAllReduce of n elements on the context's stream; kind = FEO_SUM, FEO_MAX or FEO_MIN. */
+FEO_API int feo_nccl_allreduce(feo_nccl *comm, int kind, int dtype, void *buf, size_t n);
+/* ncclAllGather: out = part 0 | part 1 | ...; bytes_per_rank is a multiple of 4. */
+FEO_API int feo_nccl_allgather(feo_nccl *comm, void *out, const void *in, size_t bytes_per_rank);
+/* Tensor::{sum,mean,var,max,min} (tensor.rs:70-307) of a leading-axis shard, leading axis removed: local partial,
+ * ncclAllReduce (var: ncclAllGather + the rank-ordered merge of feo_var_merge), epilogue.  Arguments as
+ * feo_reduce_sharded.  One process (or thread) per GPU; grouped single-thread hosts call the phases themselves. */
+FEO_API int feo_reduce_sharded_nccl(feo_nccl *comm, int kind, int dtype, void *out, const void *in, int rank, const size_t *shape,
+                            int naxes, const size_t *axes, const void *divisor_host);
+/* DynamicVector::vecmul (vector.rs:71-78) on identically sharded operands: partial dots, then ncclAllReduce. */
+FEO_API int feo_dot_sharded_nccl(feo_nccl *comm, int dtype, void *out, const void *a, const void *b, size_t batch, size_t n_local);
+/* DynamicMatrix::matmul (matrix.rs:76-90), A and B row-sharded: ncclAllGather of B (b_local = this rank's [K / world, N]
+ * panel) into scratch, then the local kernel. */
+FEO_API int feo_matmul_sharded_b_nccl(feo_nccl *comm, int algo, int dtype, void *C, const void *A, const void *b_local, size_t M,
+                              size_t K, size_t N);
+
 #ifdef __cplusplus
 }
 #endif

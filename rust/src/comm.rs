@@ -130,7 +130,10 @@ impl PeerComm {
 }
 
 impl Drop for PeerComm {
+    /// Collective, like every call on the communicator: a slower rank may still be loading this rank's slot or storing its
+    /// flag into this window, so the ranks meet in one more barrier kernel before anything is unmapped or freed.
     fn drop(&mut self) {
+        unsafe { ffi::feo_comm_barrier(self.raw) };
         self.ctx.sync();
         unsafe {
             ffi::feo_comm_destroy(self.raw);
@@ -139,5 +142,82 @@ impl Drop for PeerComm {
             }
         }
         let _ = &self.own; // freed by its own Drop, after the peers' mappings of it are no longer used by this rank
+    }
+}
+
+/// NCCL's 128-byte unique id: rank 0 creates it, the host's own rendezvous carries it to the other ranks.
+pub type NcclId = [u8; ffi::FEO_NCCL_UNIQUE_ID_BYTES];
+
+/// The NCCL route of the same exchanges (csrc/nccl_route.cu): `ncclAllReduce` after a reduction over the sharded leading
+/// axis or a dot, `ncclAllGather` of a row-sharded B in front of `matmul` -- issued inside the C ABI (libnccl.so.2 is
+/// dlopen'ed by the library), so this crate needs neither NCCL bindings nor a Python process.
+pub struct NcclComm {
+    ctx: Rc<Context>,
+    raw: *mut ffi::feo_nccl,
+    pub rank: usize,
+    pub world: usize,
+}
+
+impl NcclComm {
+    pub fn unique_id() -> NcclId {
+        let mut id = [0u8; ffi::FEO_NCCL_UNIQUE_ID_BYTES];
+        let rc = unsafe { ffi::feo_nccl_unique_id(id.as_mut_ptr()) };
+        assert!(rc == ffi::FEO_OK, "feo_nccl_unique_id failed with status {rc}: is libnccl.so.2 on the loader path (FEO_NCCL_LIB)?");
+        id
+    }
+
+    /// One process (or thread) per GPU: every rank passes the id rank 0 created (`ncclCommInitRank`).
+    pub fn new(ctx: &Rc<Context>, id: &NcclId, rank: usize, world: usize) -> NcclComm {
+        let mut raw = std::ptr::null_mut();
+        ctx.check(unsafe { ffi::feo_nccl_comm_create(ctx.raw, id.as_ptr(), rank as c_int, world as c_int, &mut raw) });
+        NcclComm { ctx: ctx.clone(), raw, rank, world }
+    }
+
+    /// `Tensor::{sum, mean, var, max, min}` (tensor.rs:70-307) of a leading-axis shard with the leading axis removed.
+    pub fn reduce<T: DeviceElem>(&self, kind: c_int, local: &DeviceTensor<T>, global_dims: &[usize], axes: &Axes) -> DeviceTensor<T> {
+        let ldims = dims_of(local.shape());
+        let mut out_rank: c_int = 0;
+        let mut out_dims = vec![0usize; global_dims.len().max(1)];
+        let rc = unsafe {
+            ffi::feo_reduce_shape(global_dims.len() as c_int, global_dims.as_ptr(), axes.len() as c_int, axes.as_ptr(), &mut out_rank, out_dims.as_mut_ptr())
+        };
+        assert!(rc == ffi::FEO_OK, "axes must be strictly ascending, unique and < order (the reference panics)");
+        out_dims.truncate(out_rank as usize);
+        let mut divisor = std::mem::MaybeUninit::<T>::uninit();
+        unsafe {
+            ffi::feo_reduce_divisor(T::DTYPE, global_dims.len() as c_int, global_dims.as_ptr(), axes.len() as c_int, axes.as_ptr(), divisor.as_mut_ptr().cast());
+        }
+        let local_axes: Vec<usize> = if axes.is_empty() { (0..ldims.len()).collect() } else { axes.clone() };
+        let out = DeviceTensor::<T>::uninit(&self.ctx, &Shape::new(out_dims).unwrap());
+        self.ctx.check(unsafe {
+            ffi::feo_reduce_sharded_nccl(self.raw, kind, T::DTYPE, out.data.ptr, local.data.ptr, ldims.len() as c_int, ldims.as_ptr(),
+                                         local_axes.len() as c_int, local_axes.as_ptr(), divisor.as_ptr().cast())
+        });
+        out
+    }
+
+    /// `DynamicVector::vecmul` (vector.rs:71-78) on two identically sharded vectors.
+    pub fn dot<T: DeviceElem>(&self, a: &DeviceTensor<T>, b: &DeviceTensor<T>) -> DeviceTensor<T> {
+        assert!(a.shape() == b.shape(), "assertion failed: self.shape() == rhs.shape()");
+        let out = DeviceTensor::<T>::uninit(&self.ctx, &Shape::new(vec![1]).unwrap());
+        self.ctx.check(unsafe { ffi::feo_dot_sharded_nccl(self.raw, T::DTYPE, out.data.ptr, a.data.ptr, b.data.ptr, 1, a.size()) });
+        out
+    }
+
+    /// `DynamicMatrix::matmul` (matrix.rs:76-90), A and B row-sharded: all-gather of B, then the local kernel.
+    pub fn matmul_sharded_b<T: DeviceElem>(&self, a_local: &DeviceTensor<T>, b_local: &DeviceTensor<T>, k: usize, n: usize) -> DeviceTensor<T> {
+        let m = dims_of(a_local.shape())[0];
+        assert_eq!(dims_of(a_local.shape())[1], k, "assertion `left == right` failed (inner dimensions)");
+        let out = DeviceTensor::<T>::uninit(&self.ctx, &Shape::new(vec![m, n]).unwrap());
+        self.ctx.check(unsafe {
+            ffi::feo_matmul_sharded_b_nccl(self.raw, ffi::FEO_MATMUL_AUTO, T::DTYPE, out.data.ptr, a_local.data.ptr, b_local.data.ptr, m, k, n)
+        });
+        out
+    }
+}
+
+impl Drop for NcclComm {
+    fn drop(&mut self) {
+        unsafe { ffi::feo_nccl_comm_destroy(self.raw) };
     }
 }

@@ -21,7 +21,7 @@ pub mod device_tensor;
 pub mod device_vector;
 pub mod ffi;
 
-pub use comm::{PeerComm, PeerHandle, PeerWindow};
+pub use comm::{NcclComm, NcclId, PeerComm, PeerHandle, PeerWindow};
 pub use context::Context;
 pub use device_matrix::DeviceMatrix;
 pub use device_storage::{DeviceElem, DeviceStorage};

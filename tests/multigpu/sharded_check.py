@@ -7,8 +7,9 @@ Every rank builds the same global tensors, uploads its block of leading rows, ru
 feotensor_b200.sharded.CudaEngine (C ABI kernels + NCCL), and compares with the same op on the whole tensor
 computed on its own GPU and with the CPU oracle: ints / max / min bit-exact, float sums within tolerance.
 
-The checks run twice: with the NCCL exchange steps and with the native peer-memory exchange kernels (csrc/peer.cu,
-`PeerComm`), whose replicated results must also be bit-identical across the ranks.
+The checks run three times: with torch.distributed's NCCL as the exchange, with the library's own NCCL route
+(csrc/nccl_route.cu, `NcclComm`: the exchange issued inside the C ABI), and with the native peer-memory exchange kernels
+(csrc/peer.cu, `PeerComm`), whose replicated results must also be bit-identical across the ranks.
 `--same-device` puts every rank on cuda:0 with gloo as the rendezvous (a one-GPU box can then exercise the IPC windows
 and the exchange kernels; the ranks' kernels time-slice, so it is a correctness run only); NCCL is skipped there.
 """
@@ -46,12 +47,17 @@ def main():
     ctx = feo.Context(local)
     comm = sharded.PeerComm(ctx)
     total = 0
-    for label, eng in (("nccl", None if args.same_device else sharded.CudaEngine(ctx)), ("peer", sharded.CudaEngine(ctx, comm=comm))):
+    ncomm = None if args.same_device else sharded.NcclComm(ctx)  # the library's own NCCL communicator (feo_nccl_*)
+    for label, eng in (("nccl", None if args.same_device else sharded.CudaEngine(ctx)),
+                       ("nccl-abi", None if args.same_device else sharded.CudaEngine(ctx, nccl=ncomm)),
+                       ("peer", sharded.CudaEngine(ctx, comm=comm))):
         if eng is not None:
             total += run_checks(feo, sharded, o, dist, ctx, eng, rank, world, label, with_gather=not args.same_device)
     ctx.sync()
     dist.barrier()
     comm.close()
+    if ncomm is not None:
+        ncomm.close()
     if rank == 0:
         print(f"sharded_check ok: world={world}, {total} checks per rank, {ctx.launch_count()} kernel launches on rank 0", flush=True)
     dist.destroy_process_group()

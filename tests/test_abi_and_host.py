@@ -38,6 +38,23 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert [lib.feo_dtype_size(i) for i in range(5)] == [4, 8, 4, 8, 4]
 
 
+def test_rust_ffi_declares_exactly_the_header():
+    """rust/ cannot be compiled in this image (no toolchain), so its `extern "C"` block is GENERATED from the header
+    (tools/gen_rust_ffi.py) and this test fails the moment the two drift apart."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_ffi.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ffi = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    assert sorted(re.findall(r"pub fn (feo_[a-z0-9_]+)\(", ffi)) == _declared_symbols()
+    # every ffi:: function the crate calls exists, and the status codes agree with the header
+    used = set()
+    for fn in os.listdir(os.path.join(ROOT, "rust", "src")):
+        used |= set(re.findall(r"ffi::(feo_[a-z0-9_]+)\(", open(os.path.join(ROOT, "rust", "src", fn)).read()))
+    assert used and used <= set(_declared_symbols()), used - set(_declared_symbols())
+    header = open(os.path.join(ROOT, "include", "feotensor_b200.h")).read()
+    for name, value in re.findall(r"pub const (FEO_[A-Z0-9_]+): c_int = (\d+);", ffi):
+        assert re.search(rf"\b{name} = {value}\b", header), f"{name} = {value} is not what the header says"
+
+
 def test_library_is_sm100a_and_uses_no_cpu_fallback():
     import feotensor_b200
     out = subprocess.run(["cuobjdump", "--list-elf", feotensor_b200.LIB_PATH], capture_output=True, text=True)

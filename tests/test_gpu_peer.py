@@ -51,3 +51,6 @@ def test_sharded_nccl_and_peer_two_gpus():
         pytest.skip("needs two GPUs")
     out = _run(_torchrun(2, "tests/multigpu/sharded_check.py"), timeout=600)
     assert "sharded_check ok: world=2" in out
+    # the one-process / G-devices model (ncclCommInitAll, grouped calls) through the C ABI alone
+    out = _run([sys.executable, "tests/multigpu/nccl_single_process.py", "--gpus", "2"], timeout=600)
+    assert "nccl_single_process ok: 2 devices" in out
