@@ -289,6 +289,288 @@ matmul_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     }
 }
 
+// =====================================================================================================================
+// The CTA-pair kernel (default): tcgen05.mma.cta_group::2 -- two CTAs of one cluster (the two SMs of a TPC) work on ONE
+// 256 x BN output tile.  CTA r of the pair holds rows [128 r, 128 r + 128) of the A tile and rows [r BN/2, (r+1) BN/2) of the
+// Bt tile in ITS shared memory and rows 128 r .. of the accumulator in ITS tensor memory; the MMA is issued by one thread of
+// the even CTA and reads both shared memories.  Against one 128 x 256 tile per CTA this cuts the operand bytes every SM
+// pulls from L2 and re-reads from shared memory by a third (64 KiB instead of 96 KiB per k-block per SM), which was what
+// bounded the single-CTA kernel (tensor pipe 78 % active, L2 -> SM at ~11 TB/s), and the smaller stage leaves room for a
+// 3-deep ring.  Everything else is the single-CTA kernel's scheme: TMA producer warp, MMA warp, 8 accumulate / epilogue warps,
+// K cut into chunks of kc k-blocks that alternate between two TMEM buffers and are added up in f32 registers with
+// round-to-nearest (the tensor core truncates inside a chunk).
+//   * persistent: the grid is min(tiles, SMs / 2) pairs; pair p works on tiles p, p + pairs, ... (grouped rasterisation), the
+//     barrier phases run on across tiles, and the next tile's MMAs start while the epilogue warps still store the last one.
+//   * BN is a run-time value (a multiple of 32, <= 256; it only enters the instruction descriptor, the TMA box and loop
+//     bounds): the host picks the BN that minimises waves x BN, e.g. 8192 x 8192 with M = 1024 rows per GPU runs as
+//     4 x 37 tiles of 256 x 224 = exactly two waves of 74 pairs instead of 128 tiles of 256 x 256 = 1.73 waves run as two.
+//   * barriers: full[s] lives in the even CTA and collects the bytes of BOTH CTAs' TMA loads (cta_group::2 loads may signal
+//     the peer's barrier); empty[s] and tmem_full[b] exist in both CTAs and are signalled by multicast tcgen05.commit;
+//     tmem_empty[b] lives in the even CTA and counts the 16 epilogue warps of the pair (the odd CTA's arrive remotely).
+constexpr int P_BM = 128;                         // rows of A (and of the accumulator) per CTA; the pair tile is 2 * P_BM x BN
+constexpr int P_BN_MAX = 256;
+constexpr int P_STAGES = 3;
+constexpr int P_TILE_A = P_BM * BK * 4;           // 16 KiB
+constexpr int P_TILE_B = (P_BN_MAX / 2) * BK * 4; // 16 KiB at BN = 256 (fixed slot size; smaller BN use a prefix)
+constexpr int P_STAGE = 2 * P_TILE_A + 2 * P_TILE_B;  // 64 KiB
+constexpr int P_SMEM = P_STAGES * P_STAGE + 1024 + 256;
+constexpr int P_GROUP_M = 8;                      // rasterisation group, in pair tiles along M
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are counted by a barrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+
+struct PairArgs {
+    float *C;
+    int M, N, BN;               // BN: pair tile width (multiple of 32, <= 256)
+    int num_k_blocks, kc;
+    int tiles_m, tiles_n;       // pair tiles: ceil(M / 256), ceil(N / BN)
+    const unsigned int *ready;  // see matmul_tf32x3_kernel
+    unsigned int ready_need;
+    int kb_rot;
+    unsigned long long peer_timeout_ns;
+    int *status;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+matmul_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                          const __grid_constant__ PairArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + P_STAGES * P_STAGE);   // used in the even CTA
+    uint64_t *empty_bar = full_bar + P_STAGES;                                       // both CTAs (multicast commit)
+    uint64_t *tmem_full_bar = empty_bar + P_STAGES;                                  // [2], both CTAs (multicast commit)
+    uint64_t *tmem_empty_bar = tmem_full_bar + 2;                                    // [2], used in the even CTA: 2 * kEpiWarps arrivals
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta = cluster_ctarank();          // 0 = even CTA (issues the MMAs), 1 = odd
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int BN = args.BN, num_k_blocks = args.num_k_blocks, kc = args.kc;
+    const int num_tiles = args.tiles_m * args.tiles_n;
+    const int num_chunks = (num_k_blocks + kc - 1) / kc;
+    const unsigned long long bar_limit = args.peer_timeout_ns ? 2 * args.peer_timeout_ns + 30000000000ull : 0;
+    const uint32_t stage_bytes_pair = 2u * (2u * P_TILE_A + 2u * (uint32_t)(BN / 2) * BK * 4u);  // both CTAs' loads of one stage
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 2 * kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
+    }
+    if (warp == 1) {  // the same warp in both CTAs: one allocation of all 512 columns in both tensor memories
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();  // barrier inits and the allocation are visible to both CTAs before anyone signals the peer
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    // tile t -> (pair-tile row, column): P_GROUP_M tiles down M before moving along N (a wave touches a near-square region)
+    auto tile_coords = [&](int t, int &tm, int &tn) {
+        const int in_group = P_GROUP_M * args.tiles_n;
+        const int first_m = (t / in_group) * P_GROUP_M;
+        const int group_m = (args.tiles_m - first_m < P_GROUP_M) ? args.tiles_m - first_m : P_GROUP_M;
+        tm = first_m + (t % in_group) % group_m;
+        tn = (t % in_group) / group_m;
+    };
+
+    if (warp == 0) {  // ===== TMA producer (one in each CTA; lane 0 issues, the warp looks ahead on the readiness flags) =====
+        uint32_t full_addr[P_STAGES];
+#pragma unroll
+        for (int s = 0; s < P_STAGES; ++s) full_addr[s] = map_to_cta(smem_u32(&full_bar[s]), 0);
+        int g = 0;  // k-block iterations issued so far, across tiles: ring slot and phase
+        for (int t = pair; t < num_tiles; t += num_pairs) {
+            int tm, tn;
+            tile_coords(t, tm, tn);
+            const int m0 = tm * 2 * P_BM + (int)cta * P_BM, n0 = tn * BN + (int)cta * (BN / 2);
+            int ready_upto = args.ready ? 0 : num_k_blocks;
+            for (int it = 0; it < num_k_blocks; ++it, ++g) {
+                if (it >= ready_upto) {
+                    const unsigned long long t0 = feo_peer::global_ns();
+                    for (;;) {
+                        bool ok = false;
+                        if (it + lane < num_k_blocks) {
+                            int kbl = it + lane + args.kb_rot;
+                            if (kbl >= num_k_blocks) kbl -= num_k_blocks;
+                            unsigned int v;
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(args.ready + kbl) : "memory");
+                            ok = v >= args.ready_need;
+                        }
+                        const unsigned int mask = __ballot_sync(0xffffffffu, ok);
+                        const int prefix = __ffs(~mask) - 1;
+                        if (prefix != 0) { ready_upto = it + (prefix < 0 ? 32 : prefix); break; }
+                        if (args.peer_timeout_ns != 0 && feo_peer::global_ns() - t0 > args.peer_timeout_ns) {
+                            if (lane == 0 && atomicOr(args.status, feo_peer::kStatusPeerTimeout) == 0)
+                                printf("matmul_tf32x3: k-block %d of B never arrived (block %d); result invalid\n", it, blockIdx.x);
+                            ready_upto = num_k_blocks;
+                            break;
+                        }
+                        __nanosleep(100);
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+                if (lane == 0) {
+                    int kb = it + args.kb_rot;
+                    if (kb >= num_k_blocks) kb -= num_k_blocks;
+                    const int s = g % P_STAGES;
+                    const uint32_t ph = (g / P_STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1, 0, bar_limit);
+                    uint8_t *st = smem + s * P_STAGE;
+                    if (cta == 0) mbar_expect_tx(&full_bar[s], stage_bytes_pair);
+                    tma_load_2d_pair(st, &map_a_hi, full_addr[s], kb * BK, m0);
+                    tma_load_2d_pair(st + P_TILE_A, &map_a_lo, full_addr[s], kb * BK, m0);
+                    tma_load_2d_pair(st + 2 * P_TILE_A, &map_b_hi, full_addr[s], kb * BK, n0);
+                    tma_load_2d_pair(st + 2 * P_TILE_A + P_TILE_B, &map_b_lo, full_addr[s], kb * BK, n0);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        if (cta == 0 && lane == 0) {  // ===== MMA issuer: one thread of the even CTA, for the pair =====
+            // kind::tf32, f32 accumulate, both operands K-major, M = 256 (the pair), N = BN
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * P_BM) >> 4) << 24);
+            int g = 0, cc = 0;  // k-block iterations / chunks so far, across tiles
+            for (int t = pair; t < num_tiles; t += num_pairs) {
+                int kb = 0;
+                for (int c = 0; c < num_chunks; ++c, ++cc) {
+                    const int buf = cc & 1;
+                    mbar_wait(&tmem_empty_bar[buf], ((cc >> 1) & 1) ^ 1, 3, bar_limit);  // both CTAs' epilogue warps have drained it
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(buf * P_BN_MAX);
+                    const int kb_end = (kb + kc < num_k_blocks) ? kb + kc : num_k_blocks;
+                    for (int first = 1; kb < kb_end; ++kb, ++g) {
+                        const int s = g % P_STAGES;
+                        const uint32_t ph = (g / P_STAGES) & 1;
+                        mbar_wait(&full_bar[s], ph, 1, bar_limit);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t st = smem_u32(smem + s * P_STAGE);
+                        const uint64_t da_hi = make_desc(st), da_lo = make_desc(st + P_TILE_A);
+                        const uint64_t db_hi = make_desc(st + 2 * P_TILE_A), db_lo = make_desc(st + 2 * P_TILE_A + P_TILE_B);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
+                            umma_tf32_pair(tmem_d, da_lo + adv, db_hi + adv, idesc, first ? 0u : 1u);
+                            first = 0;
+                            umma_tf32_pair(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
+                            umma_tf32_pair(tmem_d, da_hi + adv, db_hi + adv, idesc, 1);
+                        }
+                        umma_commit_pair(&empty_bar[s]);  // frees the ring slot in both CTAs
+                    }
+                    umma_commit_pair(&tmem_full_bar[buf]);  // chunk complete in both tensor memories
+                }
+            }
+        }
+    } else {  // ===== accumulate + epilogue: warps 2..9 of each CTA on that CTA's 128 accumulator rows =====
+        const int q = warp & 3;                 // TMEM lane quarter this warp may touch
+        const int half = (warp - 2) >> 2;       // which BN / 2 of the BN accumulator columns
+        const int hcols = BN / 2;               // a multiple of 16
+        const uint32_t empty_addr0 = map_to_cta(smem_u32(&tmem_empty_bar[0]), 0), empty_addr1 = map_to_cta(smem_u32(&tmem_empty_bar[1]), 0);
+        float acc[P_BN_MAX / 2];
+        int cc = 0;
+        for (int t = pair; t < num_tiles; t += num_pairs) {
+            int tm, tn;
+            tile_coords(t, tm, tn);
+#pragma unroll
+            for (int i = 0; i < P_BN_MAX / 2; ++i) acc[i] = 0.f;
+            for (int c = 0; c < num_chunks; ++c, ++cc) {
+                const int buf = cc & 1;
+                mbar_wait(&tmem_full_bar[buf], (cc >> 1) & 1, 2, bar_limit);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P_BN_MAX + half * hcols);
+#pragma unroll
+                for (int j = 0; j < P_BN_MAX / 2; j += 32) {
+                    if (j < hcols) {  // warp-uniform
+                        uint32_t v0[16], v1[16];
+                        const bool two = j + 16 < hcols;
+                        tmem_ld16(trow + (uint32_t)j, v0);
+                        if (two) tmem_ld16(trow + (uint32_t)(j + 16), v1);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[j + i] += __uint_as_float(v0[i]);  // round-to-nearest f32 add
+                        if (two) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) acc[j + 16 + i] += __uint_as_float(v1[i]);
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(buf ? empty_addr1 : empty_addr0);
+            }
+            // TMA zero-filled the out-of-range rows of A / Bt, so acc is well defined everywhere; only the stores are guarded
+            const int row = tm * 2 * P_BM + (int)cta * P_BM + q * 32 + lane;
+            const int col0 = tn * BN + half * hcols;
+            if (row < args.M) {
+                float *crow = args.C + (size_t)row * args.N + col0;
+                if ((args.N & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < P_BN_MAX / 2; j += 4)
+                        if (j < hcols && col0 + j < args.N) *reinterpret_cast<float4 *>(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < P_BN_MAX / 2; ++j)
+                        if (j < hcols && col0 + j < args.N) crow[j] = acc[j];
+                }
+            }
+        }
+    }
+    // neither CTA may leave (or free its tensor memory) while the peer can still signal its barriers or read its tiles
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 // ---- pre-pass: hi/lo split --------------------------------------------------------------------------------
 __device__ __forceinline__ void split1(float x, float &hi, float &lo) {
     uint32_t h;
@@ -495,17 +777,61 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
     }
 
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-    if (!make_map(&ma_hi, a_hi, M, Kp, BM) || !make_map(&ma_lo, a_lo, M, Kp, BM) || !make_map(&mb_hi, b_hi, N, Kp, BN) ||
-        !make_map(&mb_lo, b_lo, N, Kp, BN))
-        return feo_fail(ctx, FEO_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-    const size_t tiles = feo_ceil_div(N, (size_t)BN) * feo_ceil_div(M, (size_t)BM);
-    if (tiles > 0x7fffffffu) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "matmul grid too large");
-    const dim3 grid((unsigned)tiles);
     int kc = ctx->knobs[FEO_KNOB_MATMUL_TF32_KC];
     if (kc <= 0) kc = 2;  // k-blocks per TMEM accumulation chain (24 truncating accumulates), see the file header
-    matmul_tf32x3_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, (float *)C, (int)M, (int)N, num_kb, kc, ready,
-                                                                      (unsigned)feo_ceil_div(N, (size_t)GT_N), kb_rot, ctx->peer_timeout_ns, ctx->status_flag);
-    FEO_LAUNCH_CHECK(ctx);
+    if (ctx->knobs[FEO_KNOB_MATMUL_TF32_PAIR] != 1) {
+        // CTA-pair kernel: persistent over min(tiles, SMs / 2) pairs; BN = the tile width with the fewest (waves x width)
+        const int pairs_max = ctx->sm_count / 2;
+        const size_t tiles_m = feo_ceil_div(M, (size_t)(2 * P_BM));
+        int bn = ctx->knobs[FEO_KNOB_MATMUL_TF32_BN];
+        if (bn <= 0 || bn > P_BN_MAX || bn % 32 != 0) {
+            double best = 0;
+            bn = P_BN_MAX;
+            for (int cand = P_BN_MAX; cand >= 128; cand -= 32) {
+                const size_t t = tiles_m * feo_ceil_div(N, (size_t)cand);
+                // cost of a tile ~ its width plus a fixed part (narrow tiles stream A more often per flop and drain as often)
+                const double cost = (double)feo_ceil_div(t, (size_t)pairs_max) * (cand + 16);
+                if (best == 0 || cost < best * 0.985) { best = cost; bn = cand; }
+            }
+        }
+        const size_t tiles_n = feo_ceil_div(N, (size_t)bn), tiles = tiles_m * tiles_n;
+        if (tiles > 0x3fffffffu) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "matmul grid too large");
+        if (!make_map(&ma_hi, a_hi, M, Kp, P_BM) || !make_map(&ma_lo, a_lo, M, Kp, P_BM) || !make_map(&mb_hi, b_hi, N, Kp, bn / 2) ||
+            !make_map(&mb_lo, b_lo, N, Kp, bn / 2))
+            return feo_fail(ctx, FEO_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+        static bool pair_attr_set[64] = {false};
+        if (!pair_attr_set[dev]) {
+            FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_tf32x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+            pair_attr_set[dev] = true;
+        }
+        PairArgs pa{};
+        pa.C = (float *)C;
+        pa.M = (int)M;
+        pa.N = (int)N;
+        pa.BN = bn;
+        pa.num_k_blocks = num_kb;
+        pa.kc = kc;
+        pa.tiles_m = (int)tiles_m;
+        pa.tiles_n = (int)tiles_n;
+        pa.ready = ready;
+        pa.ready_need = (unsigned)feo_ceil_div(N, (size_t)GT_N);
+        pa.kb_rot = kb_rot;
+        pa.peer_timeout_ns = ctx->peer_timeout_ns;
+        pa.status = ctx->status_flag;
+        const unsigned pairs = (unsigned)(tiles < (size_t)pairs_max ? tiles : (size_t)pairs_max);
+        matmul_tf32x3_pair_kernel<<<dim3(2 * pairs), kThreads, P_SMEM, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pa);
+        FEO_LAUNCH_CHECK(ctx);
+    } else {
+        if (!make_map(&ma_hi, a_hi, M, Kp, BM) || !make_map(&ma_lo, a_lo, M, Kp, BM) || !make_map(&mb_hi, b_hi, N, Kp, BN) ||
+            !make_map(&mb_lo, b_lo, N, Kp, BN))
+            return feo_fail(ctx, FEO_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+        const size_t tiles = feo_ceil_div(N, (size_t)BN) * feo_ceil_div(M, (size_t)BM);
+        if (tiles > 0x7fffffffu) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "matmul grid too large");
+        const dim3 grid((unsigned)tiles);
+        matmul_tf32x3_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, (float *)C, (int)M, (int)N, num_kb, kc, ready,
+                                                                          (unsigned)feo_ceil_div(N, (size_t)GT_N), kb_rot, ctx->peer_timeout_ns, ctx->status_flag);
+        FEO_LAUNCH_CHECK(ctx);
+    }
     if (overlap) FEO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // the workspace is reused by the next call
     return FEO_OK;
 }
@@ -515,8 +841,7 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
 int feo_impl_matmul_tf32x3(feo_ctx *ctx, void *C, const void *A, const void *B, size_t M, size_t K, size_t N) {
     // Large products: B's split / transpose pre-pass runs on the side stream and publishes k-blocks while the matmul kernel
     // is already working on the first ones (the sharded-B machinery with a single, local panel and nothing to wait for).
-    const size_t tiles = feo_ceil_div(N, (size_t)BN) * feo_ceil_div(M, (size_t)BM);
-    if (ctx->knobs[FEO_KNOB_GATHER_OVERLAP] == 2 && tiles >= 2 * (size_t)ctx->sm_count && K >= 1024 && feo_aligned16(B)) {
+    if (ctx->knobs[FEO_KNOB_GATHER_OVERLAP] == 2 && K >= 64 && feo_aligned16(B)) {
         feo_peer::BParts parts{};
         parts.part[0] = static_cast<const float *>(B);
         parts.world = 1;

@@ -800,6 +800,41 @@ def test_matmul_tf32x3_vs_oracle(feo, oracle):
         feo.Matrix(feo.shape(4, 4), np.zeros(16, np.float32)).matmul(feo.Matrix(feo.shape(4, 4), np.zeros(16, np.float32)), algo="tf32x3")
 
 
+def test_matmul_tf32x3_kernel_variants(feo, oracle):
+    """The CTA-pair kernel (tcgen05 cta_group::2, persistent, run-time tile width BN) at every BN, the single-CTA kernel it
+    replaced (knob MATMUL_TF32_PAIR = 1), and the pre-pass overlapped with the main kernel (knob GATHER_OVERLAP = 2): each
+    inside the same f32 bound, on shapes that give a pair several tiles (persistence: barrier phases carry over), ragged
+    edges in M, N and K, an odd number of 128-row blocks (the odd CTA's rows fall outside M) and a single k-block."""
+    import feotensor_b200._lib as L
+    ctx = feo.Context.default()
+    rng = np.random.default_rng(701)
+    shapes = [(1024, 512, 8192 + 224), (2304, 160, 4000), (128, 64, 700), (385, 32, 257), (3000, 96, 3001), (640, 8192, 512)]
+    try:
+        for m, k, n in shapes:
+            A, B = rand(oracle, rng, "f32", (m, k)), rand(oracle, rng, "f32", (k, n))
+            tA, tB = feo.Matrix(feo.shape(m, k), A), feo.Matrix(feo.shape(k, n), B)
+            exact = A.astype(np.float64) @ B.astype(np.float64)
+            terms = np.abs(A.astype(np.float64)) @ np.abs(B.astype(np.float64))
+            results = {}
+            for label, pair, bn, overlap in (("pair auto", 0, 0, 0), ("pair 256", 0, 256, 0), ("pair 224", 0, 224, 0), ("pair 192", 0, 192, 0),
+                                             ("pair 160", 0, 160, 0), ("pair 128", 0, 128, 0), ("pair 96", 0, 96, 0), ("pair 32", 0, 32, 0),
+                                             ("single", 1, 0, 0), ("pair overlap", 0, 0, 2), ("pair 224 overlap", 0, 224, 2), ("no overlap", 0, 0, 1)):
+                ctx.tune(L.KNOB_MATMUL_TF32_PAIR, pair)
+                ctx.tune(L.KNOB_MATMUL_TF32_BN, bn)
+                ctx.tune(L.KNOB_GATHER_OVERLAP, overlap)
+                got = tA.matmul(tB, algo="tf32x3").to_numpy()
+                err = np.abs(got - exact)
+                assert np.all(err <= 2.0 ** -20 * terms), f"{label} {m}x{k}x{n}: max rel err {(err / terms).max():.3e} at {np.unravel_index(np.argmax(err / terms), err.shape)}"
+                results[label] = got
+            # the k order and the chunking are the same whatever the tile width: every variant produces the same bits
+            for label, got in results.items():
+                np.testing.assert_array_equal(got, results["pair auto"], err_msg=f"{label} {m}x{k}x{n}")
+    finally:
+        ctx.tune(L.KNOB_MATMUL_TF32_PAIR, 0)
+        ctx.tune(L.KNOB_MATMUL_TF32_BN, 0)
+        ctx.tune(L.KNOB_GATHER_OVERLAP, 0)
+
+
 def test_pow_and_display(feo, kat, oracle):
     """The section-8(f) rows: pow (tensor.rs:325-333; exact on the reference's own vectors, a few ulp elsewhere) and
     display (tensor.rs:507-551; host-side formatting)."""
