@@ -1,26 +1,30 @@
 #!/usr/bin/env python
-"""Error anatomy of the 3xTF32 tcgen05 matmul vs K (diagnostic; prints one line per K)."""
+"""Error anatomy of the 3xTF32 tcgen05 matmul vs K and vs the accumulation-chunk length kc (diagnostic).
+
+The tensor core truncates when it adds into the TMEM accumulator, so the error of a chain of kc k-blocks (12 kc accumulates)
+is biased toward zero and grows with kc; the kernel drains every chunk into f32 registers with round-to-nearest.  This prints,
+per K, the error on mixed-sign and on all-positive data (where the bias is one-sided) for several kc, next to the SIMT FP32
+kernel (the reference's own arithmetic, in another order)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import feotensor_b200 as feo
+import feotensor_b200._lib as L
 
+ctx = feo.Context.default()
 rng = np.random.default_rng(1)
-for k in (32, 256, 1024, 4096, 16384):
-    m, n = 128, 256
+for k in (256, 4096, 16384):
+    m, n = 256, 512
     A = rng.uniform(-1, 1, (m, k)).astype(np.float32)
     B = rng.uniform(-1, 1, (k, n)).astype(np.float32)
-    tA, tB = feo.Matrix(feo.shape(m, k), A), feo.Matrix(feo.shape(k, n), B)
-    exact = A.astype(np.float64) @ B.astype(np.float64)
-    terms = np.abs(A.astype(np.float64)) @ np.abs(B.astype(np.float64))
-    for algo in ("tf32x3", "simt"):
-        got = tA.matmul(tB, algo=algo).to_numpy().astype(np.float64)
-        err = got - exact
-        toward_zero = np.mean(np.sign(err) == -np.sign(exact))
-        print(f"K={k:6d} {algo:7s} max|err|/terms={np.max(np.abs(err) / terms):.3e}  rms err={np.sqrt(np.mean(err ** 2)):.3e}  "
-              f"mean(err*sign(exact))={np.mean(err * np.sign(exact)):+.3e}  frac toward zero={toward_zero:.3f}  rms|exact|={np.sqrt(np.mean(exact ** 2)):.2f}")
-    # all-positive data: every partial sum is positive, so truncation bias is one-sided
-    Ap, Bp = np.abs(A), np.abs(B)
-    got = feo.Matrix(feo.shape(m, k), Ap).matmul(feo.Matrix(feo.shape(k, n), Bp), algo="tf32x3").to_numpy().astype(np.float64)
-    ex = Ap.astype(np.float64) @ Bp.astype(np.float64)
-    print(f"K={k:6d} positive data: mean rel err={np.mean((got - ex) / ex):+.3e}  max rel={np.max(np.abs(got - ex) / ex):.3e}")
+    for label, Ax, Bx in (("mixed", A, B), ("positive", np.abs(A), np.abs(B))):
+        tA, tB = feo.Matrix(feo.shape(m, k), Ax), feo.Matrix(feo.shape(k, n), Bx)
+        exact = Ax.astype(np.float64) @ Bx.astype(np.float64)
+        terms = np.abs(Ax.astype(np.float64)) @ np.abs(Bx.astype(np.float64))
+        for algo, kc in [("simt", 0)] + [("tf32x3", c) for c in (1, 2, 3, 4, 6, 8, 16)]:
+            ctx.tune(L.KNOB_MATMUL_TF32_KC, kc)
+            got = tA.matmul(tB, algo=algo).to_numpy().astype(np.float64)
+            err = got - exact
+            print(f"K={k:6d} {label:8s} {algo:7s} kc={kc:2d} max|err|/terms={np.max(np.abs(err) / terms):.3e}  mean(err/terms)={np.mean(err / terms):+.3e}  "
+                  f"rms(err/terms)={np.sqrt(np.mean((err / terms) ** 2)):.3e}  frac toward zero={np.mean(np.sign(err) == -np.sign(exact)):.3f}")
+ctx.tune(L.KNOB_MATMUL_TF32_KC, 0)
