@@ -96,6 +96,21 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
     return d;
 }
+// MN-major descriptor for a raw tile of B[K,N].  For 32-bit operands the tensor core transposes MN-major data only from the
+// "128-byte swizzle with 32-byte atoms" layout (UMMA layout type 1, TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 32
+// consecutive n (128 bytes), the four 32-byte chunks of a row XOR-ed with (k mod 4), i.e. a 4-row, 512-byte swizzle atom.
+// Canonical layout ((8,n),(4,k)):((1,LBO),(8,SBO)) in 16-byte units: leading byte offset = stride between 32-column groups
+// (one TMA box, P_BOX_BYTES), stride byte offset = stride between 4-row k groups (512); one UMMA_K step (8 k) = two atoms,
+// so the start address advances 1024 bytes per step.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t group_stride_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(group_stride_bytes >> 4) << 16;      // leading byte offset: next 32 columns
+    d |= (uint64_t)(512 >> 4) << 32;                     // stride byte offset: next 4 k-rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                              // SWIZZLE_128B_BASE32B
+    return d;
+}
 // kind::tf32, f32 accumulate, both operands K-major, M = 128, N = 256.
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -291,30 +306,43 @@ matmul_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 
 // =====================================================================================================================
 // The CTA-pair kernel (default): tcgen05.mma.cta_group::2 -- two CTAs of one cluster (the two SMs of a TPC) work on ONE
-// 256 x BN output tile.  CTA r of the pair holds rows [128 r, 128 r + 128) of the A tile and rows [r BN/2, (r+1) BN/2) of the
-// Bt tile in ITS shared memory and rows 128 r .. of the accumulator in ITS tensor memory; the MMA is issued by one thread of
+// 256 x BN output tile.  CTA r of the pair holds rows [128 r, 128 r + 128) of the A tile and columns [r BN/2, (r+1) BN/2) of the
+// B tile in ITS shared memory and rows 128 r .. of the accumulator in ITS tensor memory; the MMA is issued by one thread of
 // the even CTA and reads both shared memories.  Against one 128 x 256 tile per CTA this cuts the operand bytes every SM
-// pulls from L2 and re-reads from shared memory by a third (64 KiB instead of 96 KiB per k-block per SM), which was what
-// bounded the single-CTA kernel (tensor pipe 78 % active, L2 -> SM at ~11 TB/s), and the smaller stage leaves room for a
-// 3-deep ring.  Everything else is the single-CTA kernel's scheme: TMA producer warp, MMA warp, 8 accumulate / epilogue warps,
-// K cut into chunks of kc k-blocks that alternate between two TMEM buffers and are added up in f32 registers with
-// round-to-nearest (the tensor core truncates inside a chunk).
+// pulls from L2 and re-reads from shared memory by a third, which was what bounded the single-CTA kernel (tensor pipe 78 %
+// active, L2 -> SM at ~11 TB/s), and the smaller stage leaves room for a 3-deep ring.  K is cut into chunks of kc k-blocks
+// that alternate between two TMEM buffers and are added up in f32 registers with round-to-nearest (the tensor core truncates
+// inside a chunk).
 //   * persistent: the grid is min(tiles, SMs / 2) pairs; pair p works on tiles p, p + pairs, ... (grouped rasterisation), the
 //     barrier phases run on across tiles, and the next tile's MMAs start while the epilogue warps still store the last one.
 //   * BN is a run-time value (a multiple of 32, <= 256; it only enters the instruction descriptor, the TMA box and loop
 //     bounds): the host picks the BN that minimises waves x BN, e.g. 8192 x 8192 with M = 1024 rows per GPU runs as
 //     4 x 37 tiles of 256 x 224 = exactly two waves of 74 pairs instead of 128 tiles of 256 x 256 = 1.73 waves run as two.
-//   * barriers: full[s] lives in the even CTA and collects the bytes of BOTH CTAs' TMA loads (cta_group::2 loads may signal
-//     the peer's barrier); empty[s] and tmem_full[b] exist in both CTAs and are signalled by multicast tcgen05.commit;
-//     tmem_empty[b] lives in the even CTA and counts the 16 epilogue warps of the pair (the odd CTA's arrive remotely).
+//   * RAW_B (default when N % 4 == 0): B is never pre-processed.  TMA brings raw f32 tiles of B[K,N] -- boxes of 32 columns
+//     x 32 k-rows with the 128-byte / 32-byte-atom swizzle, i.e. the MN-major ("transposed") tf32 operand layout of tcgen05 -- into shared
+//     memory, two warps of each CTA split them in place (hi over the raw tile, lo into a second buffer; the swizzle is
+//     irrelevant to an elementwise pass), fence them for the async proxy and arrive on the stage's barrier; the MMA reads B
+//     MN-major (instruction-descriptor bit 16).  This removes the split + transpose pre-pass over B (768 MB of traffic and
+//     ~115 us at 8192 x 8192 -- a fifth of the whole call for a 1024-row share of A at 8 GPUs) and halves B's L2 -> SM
+//     stream.  A keeps its cheap row pre-pass (A_hi | A_lo, K-major): splitting it in the kernel too would put the shared-
+//     memory pipe at ~95 % (the MMAs alone read 64 B/cycle of its 128).
+//   * barriers: full[s] lives in the even CTA and collects the bytes of BOTH CTAs' A loads (cta_group::2 loads may signal
+//     the peer's barrier) plus, with RAW_B, one arrival per splitting warp of the pair; raw[s] (RAW_B) is per CTA and
+//     collects that CTA's raw-B bytes; empty[s] and tmem_full[b] exist in both CTAs and are signalled by multicast
+//     tcgen05.commit; tmem_empty[b] lives in the even CTA and counts the 16 epilogue warps of the pair.
 constexpr int P_BM = 128;                         // rows of A (and of the accumulator) per CTA; the pair tile is 2 * P_BM x BN
 constexpr int P_BN_MAX = 256;
 constexpr int P_STAGES = 3;
 constexpr int P_TILE_A = P_BM * BK * 4;           // 16 KiB
 constexpr int P_TILE_B = (P_BN_MAX / 2) * BK * 4; // 16 KiB at BN = 256 (fixed slot size; smaller BN use a prefix)
-constexpr int P_STAGE = 2 * P_TILE_A + 2 * P_TILE_B;  // 64 KiB
+constexpr int P_STAGE = 2 * P_TILE_A + 2 * P_TILE_B;  // 64 KiB: A_hi | A_lo | B_hi (raw B lands here) | B_lo
 constexpr int P_SMEM = P_STAGES * P_STAGE + 1024 + 256;
 constexpr int P_GROUP_M = 8;                      // rasterisation group, in pair tiles along M
+constexpr int P_THREADS = 384;                    // warp 0 TMA, warp 1 MMA, warps 2-3 split raw B, warps 4-11 accumulate + epilogue
+constexpr int P_SPLIT_WARPS = 2;
+constexpr int P_EPI_WARP0 = 4;
+constexpr int P_BOX_N = 32;                       // raw-B TMA box: 32 columns (one 128-byte swizzle row) x BK k-rows
+constexpr int P_BOX_BYTES = P_BOX_N * BK * 4;     // 4 KiB = four 8-row swizzle atoms, one per UMMA_K step
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -331,8 +359,13 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
     return r;
 }
+// Arrive on a barrier in (possibly) the peer CTA.  Deliberately NOT .release.cluster: that form compiles to MEMBAR.ALL.GPU +
+// ERRBAR in front of the arrive -- ~1700 cycles per hand-off, measured (profiles/r2_matmul_drain.md): it made the chunk drain
+// the critical path (85 % of the tensor pipe's cycles at kc = 2, 97 % without it).  What is handed over here is tensor memory
+// (loads completed by tcgen05.wait::ld, ordered by the tcgen05 fences on both sides) or shared memory already fenced for the
+// async proxy, so the default form -- the one CUTLASS uses for the same hand-offs -- is enough.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's shared memory whose bytes are counted by a barrier that may live in the peer CTA
 __device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1) {
@@ -355,12 +388,26 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
                  : "memory");
 }
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t (&v)[4]) {
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint32_t (&v)[4]) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
           "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
+}
+
+// x = hi + lo exactly: hi = x rounded to TF32 (ptxas: add 0x1000, clear 13 bits), lo = the remainder (<= 13 significant bits)
+__device__ __forceinline__ void split1(float x, float &hi, float &lo) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    lo = x - hi;
 }
 
 struct PairArgs {
@@ -375,15 +422,17 @@ struct PairArgs {
     int *status;
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+template <bool RAW_B>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 matmul_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                          const __grid_constant__ CUtensorMap map_b_hi /* RAW_B: the raw B[K,N] */, const __grid_constant__ CUtensorMap map_b_lo,
                           const __grid_constant__ PairArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + P_STAGES * P_STAGE);   // used in the even CTA
     uint64_t *empty_bar = full_bar + P_STAGES;                                       // both CTAs (multicast commit)
-    uint64_t *tmem_full_bar = empty_bar + P_STAGES;                                  // [2], both CTAs (multicast commit)
+    uint64_t *raw_bar = empty_bar + P_STAGES;                                        // RAW_B: this CTA's raw-B bytes have landed
+    uint64_t *tmem_full_bar = raw_bar + P_STAGES;                                    // [2], both CTAs (multicast commit)
     uint64_t *tmem_empty_bar = tmem_full_bar + 2;                                    // [2], used in the even CTA: 2 * kEpiWarps arrivals
     uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
 
@@ -394,16 +443,22 @@ matmul_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
     const int num_tiles = args.tiles_m * args.tiles_n;
     const int num_chunks = (num_k_blocks + kc - 1) / kc;
     const unsigned long long bar_limit = args.peer_timeout_ns ? 2 * args.peer_timeout_ns + 30000000000ull : 0;
-    const uint32_t stage_bytes_pair = 2u * (2u * P_TILE_A + 2u * (uint32_t)(BN / 2) * BK * 4u);  // both CTAs' loads of one stage
+    const int nbox = (BN / 2 + P_BOX_N - 1) / P_BOX_N;  // RAW_B: 32-column boxes per CTA and k-block (the last may overhang the tile)
+    // bytes the even CTA's full[s] collects per stage: both CTAs' A tiles, and both CTAs' pre-split B tiles unless RAW_B
+    const uint32_t full_tx_bytes = RAW_B ? 2u * (2u * P_TILE_A) : 2u * (2u * P_TILE_A + 2u * (uint32_t)(BN / 2) * BK * 4u);
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < P_STAGES; ++s) {
+            mbar_init(&full_bar[s], RAW_B ? 1 + 2 * P_SPLIT_WARPS : 1);
+            mbar_init(&empty_bar[s], 1);
+            mbar_init(&raw_bar[s], 1);
+        }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 2 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
+        if (!RAW_B) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
     }
     if (warp == 1) {  // the same warp in both CTAs: one allocation of all 512 columns in both tensor memories
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(kTmemCols) : "memory");
@@ -465,19 +520,28 @@ matmul_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                     const uint32_t ph = (g / P_STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1, 0, bar_limit);
                     uint8_t *st = smem + s * P_STAGE;
-                    if (cta == 0) mbar_expect_tx(&full_bar[s], stage_bytes_pair);
+                    if (cta == 0) mbar_expect_tx(&full_bar[s], full_tx_bytes);
                     tma_load_2d_pair(st, &map_a_hi, full_addr[s], kb * BK, m0);
                     tma_load_2d_pair(st + P_TILE_A, &map_a_lo, full_addr[s], kb * BK, m0);
-                    tma_load_2d_pair(st + 2 * P_TILE_A, &map_b_hi, full_addr[s], kb * BK, n0);
-                    tma_load_2d_pair(st + 2 * P_TILE_A + P_TILE_B, &map_b_lo, full_addr[s], kb * BK, n0);
+                    if (RAW_B) {
+                        mbar_expect_tx(&raw_bar[s], (uint32_t)nbox * P_BOX_BYTES);
+                        for (int i = 0; i < nbox; ++i)  // coordinates: (column, k-row) of B[K,N]
+                            tma_load_2d(st + 2 * P_TILE_A + i * P_BOX_BYTES, &map_b_hi, &raw_bar[s], n0 + i * P_BOX_N, kb * BK);
+                    } else {
+                        tma_load_2d_pair(st + 2 * P_TILE_A, &map_b_hi, full_addr[s], kb * BK, n0);
+                        tma_load_2d_pair(st + 2 * P_TILE_A + P_TILE_B, &map_b_lo, full_addr[s], kb * BK, n0);
+                    }
                 }
                 __syncwarp();
             }
         }
     } else if (warp == 1) {
         if (cta == 0 && lane == 0) {  // ===== MMA issuer: one thread of the even CTA, for the pair =====
-            // kind::tf32, f32 accumulate, both operands K-major, M = 256 (the pair), N = BN
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * P_BM) >> 4) << 24);
+            // kind::tf32, f32 accumulate, A K-major, B K-major (pre-split) or MN-major (RAW_B), M = 256 (the pair), N = BN
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (RAW_B ? (1u << 16) : 0u) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)((2 * P_BM) >> 4) << 24);
+            // descriptor step per UMMA_K: 32 bytes along a K-major row; one 1024-byte swizzle atom of an MN-major tile
+            const uint64_t a_step = (uint64_t)((UMMA_K * 4) >> 4), b_step = RAW_B ? (uint64_t)(1024 >> 4) : a_step;
             int g = 0, cc = 0;  // k-block iterations / chunks so far, across tiles
             for (int t = pair; t < num_tiles; t += num_pairs) {
                 int kb = 0;
@@ -494,14 +558,15 @@ matmul_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t st = smem_u32(smem + s * P_STAGE);
                         const uint64_t da_hi = make_desc(st), da_lo = make_desc(st + P_TILE_A);
-                        const uint64_t db_hi = make_desc(st + 2 * P_TILE_A), db_lo = make_desc(st + 2 * P_TILE_A + P_TILE_B);
+                        const uint64_t db_hi = RAW_B ? make_desc_mn(st + 2 * P_TILE_A, P_BOX_BYTES) : make_desc(st + 2 * P_TILE_A);
+                        const uint64_t db_lo = RAW_B ? make_desc_mn(st + 2 * P_TILE_A + P_TILE_B, P_BOX_BYTES) : make_desc(st + 2 * P_TILE_A + P_TILE_B);
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
-                            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
-                            umma_tf32_pair(tmem_d, da_lo + adv, db_hi + adv, idesc, first ? 0u : 1u);
+                            const uint64_t adv_a = (uint64_t)k * a_step, adv_b = (uint64_t)k * b_step;
+                            umma_tf32_pair(tmem_d, da_lo + adv_a, db_hi + adv_b, idesc, first ? 0u : 1u);
                             first = 0;
-                            umma_tf32_pair(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
-                            umma_tf32_pair(tmem_d, da_hi + adv, db_hi + adv, idesc, 1);
+                            umma_tf32_pair(tmem_d, da_hi + adv_a, db_lo + adv_b, idesc, 1);
+                            umma_tf32_pair(tmem_d, da_hi + adv_a, db_hi + adv_b, idesc, 1);
                         }
                         umma_commit_pair(&empty_bar[s]);  // frees the ring slot in both CTAs
                     }
@@ -509,9 +574,44 @@ matmul_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                 }
             }
         }
-    } else {  // ===== accumulate + epilogue: warps 2..9 of each CTA on that CTA's 128 accumulator rows =====
-        const int q = warp & 3;                 // TMEM lane quarter this warp may touch
-        const int half = (warp - 2) >> 2;       // which BN / 2 of the BN accumulator columns
+    } else if (warp < P_EPI_WARP0) {
+        if (RAW_B) {  // ===== split the raw B tile in place: hi = rna_tf32(b) over the raw values, lo = b - hi beside it =====
+            const int tid = (int)threadIdx.x - 64;  // 0 .. 63
+            uint32_t full_addr[P_STAGES];
+#pragma unroll
+            for (int s = 0; s < P_STAGES; ++s) full_addr[s] = map_to_cta(smem_u32(&full_bar[s]), 0);
+            int g = 0;
+            for (int t = pair; t < num_tiles; t += num_pairs) {
+                for (int it = 0; it < num_k_blocks; ++it, ++g) {
+                    const int s = g % P_STAGES;
+                    const uint32_t ph = (g / P_STAGES) & 1;
+                    mbar_wait(&raw_bar[s], ph, 4, bar_limit);
+                    const uint32_t hi_addr = smem_u32(smem + s * P_STAGE + 2 * P_TILE_A) + (uint32_t)tid * 16u, lo_addr = hi_addr + P_TILE_B;
+                    for (int b = 0; b < nbox; ++b) {
+                        uint32_t v[4][4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) lds128(hi_addr + (uint32_t)(b * P_BOX_BYTES + j * 1024), v[j]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t h[4], l[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                h[e] = (v[j][e] + 0x1000u) & 0xffffe000u;  // cvt.rna.tf32.f32 for finite values (what ptxas emits for it)
+                                l[e] = __float_as_uint(__uint_as_float(v[j][e]) - __uint_as_float(h[e]));
+                            }
+                            sts128(hi_addr + (uint32_t)(b * P_BOX_BYTES + j * 1024), h);
+                            sts128(lo_addr + (uint32_t)(b * P_BOX_BYTES + j * 1024), l);
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core's reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(full_addr[s]);
+                }
+            }
+        }
+    } else {  // ===== accumulate + epilogue: 8 warps of each CTA on that CTA's 128 accumulator rows =====
+        const int q = warp & 3;                           // TMEM lane quarter this warp may touch
+        const int half = (warp - P_EPI_WARP0) >> 2;       // which BN / 2 of the BN accumulator columns
         const int hcols = BN / 2;               // a multiple of 16
         const uint32_t empty_addr0 = map_to_cta(smem_u32(&tmem_empty_bar[0]), 0), empty_addr1 = map_to_cta(smem_u32(&tmem_empty_bar[1]), 0);
         float acc[P_BN_MAX / 2];
@@ -527,26 +627,20 @@ matmul_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * P_BN_MAX + half * hcols);
 #pragma unroll
-                for (int j = 0; j < P_BN_MAX / 2; j += 32) {
-                    if (j < hcols) {  // warp-uniform
-                        uint32_t v0[16], v1[16];
-                        const bool two = j + 16 < hcols;
-                        tmem_ld16(trow + (uint32_t)j, v0);
-                        if (two) tmem_ld16(trow + (uint32_t)(j + 16), v1);
+                for (int j = 0; j < P_BN_MAX / 2; j += 16) {
+                    if (j < hcols) {  // warp-uniform; the eight warps' loads share one 64 B/cycle TMEM read port, so one in flight each is enough
+                        uint32_t v[16];
+                        tmem_ld16(trow + (uint32_t)j, v);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) acc[j + i] += __uint_as_float(v0[i]);  // round-to-nearest f32 add
-                        if (two) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) acc[j + 16 + i] += __uint_as_float(v1[i]);
-                        }
+                        for (int i = 0; i < 16; ++i) acc[j + i] += __uint_as_float(v[i]);  // round-to-nearest f32 add
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(buf ? empty_addr1 : empty_addr0);
             }
-            // TMA zero-filled the out-of-range rows of A / Bt, so acc is well defined everywhere; only the stores are guarded
+            // TMA zero-filled the out-of-range rows of A / B, so acc is well defined everywhere; only the stores are guarded
             const int row = tm * 2 * P_BM + (int)cta * P_BM + q * 32 + lane;
             const int col0 = tn * BN + half * hcols;
             if (row < args.M) {
@@ -572,12 +666,6 @@ matmul_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
 }
 
 // ---- pre-pass: hi/lo split --------------------------------------------------------------------------------
-__device__ __forceinline__ void split1(float x, float &hi, float &lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
-    lo = x - hi;
-}
 // A[M,K] -> hi/lo [M,Kp] (Kp = K rounded up to BK, zero padded).
 __global__ void __launch_bounds__(256) split_rows_kernel(float *__restrict__ hi, float *__restrict__ lo, const float *__restrict__ x, int M, int K, int Kp, bool vec) {
     const size_t nvec = (size_t)M * (Kp / 4);
@@ -685,6 +773,44 @@ __global__ void __launch_bounds__(256, 6) split_transpose_gather_kernel(float *_
     }
 }
 
+// RAW_B with a row-sharded B: the panels are pulled over NVLink into ONE local raw copy of B[K,N] (no split, no transpose --
+// the matmul kernel does that on the tiles), k-blocks in the same rotated order, one ready[] count per k-block and CTA.
+// A CTA moves 32 k-rows x 1024 columns; every thread keeps 8 sixteen-byte peer loads in flight.
+constexpr int GR_COLS = 1024;
+__global__ void __launch_bounds__(256) gather_rows_kernel(float *__restrict__ braw, const __grid_constant__ feo_peer::BParts parts,
+                                                          const __grid_constant__ feo_peer::XchgParams sync, int K, int N, int kb_rot,
+                                                          unsigned int *__restrict__ ready) {
+    feo_peer::signal_and_wait(sync);
+    int kblock = blockIdx.y + kb_rot;
+    if (kblock >= (int)gridDim.y) kblock -= gridDim.y;
+    const int k0 = kblock * GT_K, n = blockIdx.x * GR_COLS + threadIdx.x * 4;
+    if (n < N) {  // N % 4 == 0: whole vectors
+#pragma unroll
+        for (int r0 = 0; r0 < GT_K; r0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = k0 + r0 + j;
+                if (k < K) {
+                    const int r = k / parts.rows_per_part;
+                    v[j] = feo_peer::ld_peer(reinterpret_cast<const float4 *>(parts.part[r] + (size_t)(k - r * parts.rows_per_part) * N + n));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = k0 + r0 + j;
+                if (k < K) *reinterpret_cast<float4 *>(braw + (size_t)k * N + n) = v[j];
+            }
+        }
+    }
+    if (ready) {
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(ready + kblock, 1u);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -700,8 +826,9 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D row-major [rows, K] f32 tensor, box = BK x box_rows, 128-byte swizzle.
-bool make_map(CUtensorMap *map, const float *base, size_t rows, size_t K, int box_rows) {
+// 2-D row-major [rows, K] f32 tensor, box = BK x box_rows, 128-byte swizzle (16-byte atoms for K-major operands, 32-byte
+// atoms for the raw MN-major B).
+bool make_map(CUtensorMap *map, const float *base, size_t rows, size_t K, int box_rows, bool atom32 = false) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -709,7 +836,8 @@ bool make_map(CUtensorMap *map, const float *base, size_t rows, size_t K, int bo
     const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace
@@ -726,52 +854,69 @@ namespace {
 int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const feo_peer::BParts *parts, const feo_peer::XchgParams *sync,
                       size_t M, size_t K, size_t N) {
     if (!feo_aligned16(A) || !feo_aligned16(C) || (B && !feo_aligned16(B))) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "TF32X3 needs 16-byte aligned operands");
+    const bool pair = ctx->knobs[FEO_KNOB_MATMUL_TF32_PAIR] != 1;
+    // RAW_B: the CTA-pair kernel reads B as it lies in memory and splits it on the fly (TMA needs a 16-byte row pitch)
+    bool raw_b = pair && ctx->knobs[FEO_KNOB_MATMUL_TF32_BRAW] != 1 && N % 4 == 0;
+    if (parts)
+        for (int r = 0; r < parts->world; ++r) raw_b = raw_b && feo_aligned16(parts->part[r]);
     static bool attr_set[64] = {false};  // the opt-in is per device
     const int dev = ctx->device & 63;
     if (!attr_set[dev]) {
         FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_tf32x3_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+        FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_tf32x3_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
         attr_set[dev] = true;
     }
-    // workspace: A_hi | A_lo [M,Kp]  and  Bt_hi | Bt_lo [N,Kp], Kp = K rounded up to one k-block
+    // workspace: A_hi | A_lo [M,Kp], then either Bt_hi | Bt_lo [N,Kp] (pre-pass) or, for RAW_B with a sharded B, the gathered
+    // raw B [K,N]; Kp = K rounded up to one k-block; then one readiness counter per k-block
     const size_t Kp = (K + BK - 1) / BK * BK;
     void *ws = nullptr;
-    const size_t a_elems = M * Kp, b_elems = N * Kp;
-    int rc = feo_workspace(ctx, (2 * a_elems + 2 * b_elems) * sizeof(float) + (Kp / BK) * sizeof(unsigned int), &ws);
+    const size_t a_elems = M * Kp, b_elems = raw_b ? (parts ? K * N : 0) : 2 * N * Kp;
+    int rc = feo_workspace(ctx, (2 * a_elems + b_elems) * sizeof(float) + (Kp / BK) * sizeof(unsigned int), &ws);
     if (rc != FEO_OK) return rc;
-    float *a_hi = (float *)ws, *a_lo = a_hi + a_elems, *b_hi = a_lo + a_elems, *b_lo = b_hi + b_elems;
+    float *a_hi = (float *)ws, *a_lo = a_hi + a_elems, *b_ws = a_lo + a_elems;
+    float *b_hi = b_ws, *b_lo = raw_b ? nullptr : b_ws + N * Kp;
+    unsigned int *ready_ws = reinterpret_cast<unsigned int *>(b_ws + b_elems);
     const int num_kb = (int)(Kp / BK);
     static_assert(GT_K == BK, "one gather tile row = one k-block of the main kernel");
 
-    // B arriving from peers: the pre-pass goes to a high-priority side stream and the main kernel consumes k-blocks as
+    // B arriving from peers: the gather goes to a high-priority side stream and the main kernel consumes k-blocks as
     // they are published (knob FEO_KNOB_GATHER_OVERLAP = 1: plain stream order instead)
     unsigned int *ready = nullptr;
+    unsigned int ready_need = 0;
     int kb_rot = 0;
     bool overlap = false;
     if (parts) {
         kb_rot = (int)(((size_t)sync->rank * parts->rows_per_part) / BK);
         overlap = ctx->knobs[FEO_KNOB_GATHER_OVERLAP] != 1 && feo_side_stream(ctx) == FEO_OK;
-        bool vec = N % 4 == 0;
-        for (int r = 0; r < parts->world; ++r) vec = vec && feo_aligned16(parts->part[r]);
-        const dim3 ggrid((unsigned)feo_ceil_div(N, (size_t)GT_N), (unsigned)num_kb);
+        cudaStream_t gstream = ctx->stream;
         if (overlap) {
-            ready = reinterpret_cast<unsigned int *>(b_lo + b_elems);
+            ready = ready_ws;
             FEO_CUDA(ctx, cudaMemsetAsync(ready, 0, (size_t)num_kb * sizeof(unsigned int), ctx->stream));
             FEO_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
             FEO_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
-            split_transpose_gather_kernel<<<ggrid, 256, 0, ctx->side_stream>>>(b_hi, b_lo, *parts, *sync, (int)K, (int)N, (int)Kp, vec, kb_rot, ready);
-            FEO_LAUNCH_CHECK(ctx);
-            FEO_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
-        } else {
-            split_transpose_gather_kernel<<<ggrid, 256, 0, ctx->stream>>>(b_hi, b_lo, *parts, *sync, (int)K, (int)N, (int)Kp, vec, kb_rot, nullptr);
-            FEO_LAUNCH_CHECK(ctx);
+            gstream = ctx->side_stream;
         }
+        if (raw_b) {
+            const dim3 ggrid((unsigned)feo_ceil_div(N, (size_t)GR_COLS), (unsigned)num_kb);
+            ready_need = ggrid.x;
+            gather_rows_kernel<<<ggrid, 256, 0, gstream>>>(b_ws, *parts, *sync, (int)K, (int)N, kb_rot, ready);
+        } else {
+            bool vec = N % 4 == 0;
+            for (int r = 0; r < parts->world; ++r) vec = vec && feo_aligned16(parts->part[r]);
+            const dim3 ggrid((unsigned)feo_ceil_div(N, (size_t)GT_N), (unsigned)num_kb);
+            ready_need = ggrid.x;
+            split_transpose_gather_kernel<<<ggrid, 256, 0, gstream>>>(b_hi, b_lo, *parts, *sync, (int)K, (int)N, (int)Kp, vec, kb_rot, ready);
+        }
+        FEO_LAUNCH_CHECK(ctx);
+        if (overlap) FEO_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
     }
 
     size_t blocks = feo_ceil_div(a_elems / 4, (size_t)256);
     if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
     split_rows_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a_hi, a_lo, (const float *)A, (int)M, (int)K, (int)Kp, K % 4 == 0);
     FEO_LAUNCH_CHECK(ctx);
-    if (!parts) {
+    if (!parts && !raw_b) {
         split_transpose_kernel<<<dim3((unsigned)feo_ceil_div(N, (size_t)32), (unsigned)(Kp / 32)), 256, 0, ctx->stream>>>(b_hi, b_lo, (const float *)B, (int)K, (int)N, (int)Kp);
         FEO_LAUNCH_CHECK(ctx);
     }
@@ -779,7 +924,7 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int kc = ctx->knobs[FEO_KNOB_MATMUL_TF32_KC];
     if (kc <= 0) kc = 2;  // k-blocks per TMEM accumulation chain (24 truncating accumulates), see the file header
-    if (ctx->knobs[FEO_KNOB_MATMUL_TF32_PAIR] != 1) {
+    if (pair) {
         // CTA-pair kernel: persistent over min(tiles, SMs / 2) pairs; BN = the tile width with the fewest (waves x width)
         const int pairs_max = ctx->sm_count / 2;
         const size_t tiles_m = feo_ceil_div(M, (size_t)(2 * P_BM));
@@ -796,14 +941,15 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
         }
         const size_t tiles_n = feo_ceil_div(N, (size_t)bn), tiles = tiles_m * tiles_n;
         if (tiles > 0x3fffffffu) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "matmul grid too large");
-        if (!make_map(&ma_hi, a_hi, M, Kp, P_BM) || !make_map(&ma_lo, a_lo, M, Kp, P_BM) || !make_map(&mb_hi, b_hi, N, Kp, bn / 2) ||
-            !make_map(&mb_lo, b_lo, N, Kp, bn / 2))
-            return feo_fail(ctx, FEO_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-        static bool pair_attr_set[64] = {false};
-        if (!pair_attr_set[dev]) {
-            FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_tf32x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
-            pair_attr_set[dev] = true;
+        bool ok = make_map(&ma_hi, a_hi, M, Kp, P_BM) && make_map(&ma_lo, a_lo, M, Kp, P_BM);
+        if (raw_b) {
+            // B[K,N] (or its gathered copy) as it lies: inner dimension N, boxes of 32 columns x 32 k-rows; rows >= K read as zero
+            ok = ok && make_map(&mb_hi, parts ? b_ws : (const float *)B, K, N, BK, true);
+            mb_lo = mb_hi;
+        } else {
+            ok = ok && make_map(&mb_hi, b_hi, N, Kp, bn / 2) && make_map(&mb_lo, b_lo, N, Kp, bn / 2);
         }
+        if (!ok) return feo_fail(ctx, FEO_ERR_CUDA, "cuTensorMapEncodeTiled failed");
         PairArgs pa{};
         pa.C = (float *)C;
         pa.M = (int)M;
@@ -814,12 +960,15 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
         pa.tiles_m = (int)tiles_m;
         pa.tiles_n = (int)tiles_n;
         pa.ready = ready;
-        pa.ready_need = (unsigned)feo_ceil_div(N, (size_t)GT_N);
+        pa.ready_need = ready_need;
         pa.kb_rot = kb_rot;
         pa.peer_timeout_ns = ctx->peer_timeout_ns;
         pa.status = ctx->status_flag;
         const unsigned pairs = (unsigned)(tiles < (size_t)pairs_max ? tiles : (size_t)pairs_max);
-        matmul_tf32x3_pair_kernel<<<dim3(2 * pairs), kThreads, P_SMEM, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pa);
+        if (raw_b)
+            matmul_tf32x3_pair_kernel<true><<<dim3(2 * pairs), P_THREADS, P_SMEM, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pa);
+        else
+            matmul_tf32x3_pair_kernel<false><<<dim3(2 * pairs), P_THREADS, P_SMEM, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pa);
         FEO_LAUNCH_CHECK(ctx);
     } else {
         if (!make_map(&ma_hi, a_hi, M, Kp, BM) || !make_map(&ma_lo, a_lo, M, Kp, BM) || !make_map(&mb_hi, b_hi, N, Kp, BN) ||
@@ -829,7 +978,7 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
         if (tiles > 0x7fffffffu) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "matmul grid too large");
         const dim3 grid((unsigned)tiles);
         matmul_tf32x3_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, (float *)C, (int)M, (int)N, num_kb, kc, ready,
-                                                                          (unsigned)feo_ceil_div(N, (size_t)GT_N), kb_rot, ctx->peer_timeout_ns, ctx->status_flag);
+                                                                          ready_need, kb_rot, ctx->peer_timeout_ns, ctx->status_flag);
         FEO_LAUNCH_CHECK(ctx);
     }
     if (overlap) FEO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // the workspace is reused by the next call
@@ -839,17 +988,6 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
 }  // namespace
 
 int feo_impl_matmul_tf32x3(feo_ctx *ctx, void *C, const void *A, const void *B, size_t M, size_t K, size_t N) {
-    // Large products: B's split / transpose pre-pass runs on the side stream and publishes k-blocks while the matmul kernel
-    // is already working on the first ones (the sharded-B machinery with a single, local panel and nothing to wait for).
-    if (ctx->knobs[FEO_KNOB_GATHER_OVERLAP] == 2 && K >= 64 && feo_aligned16(B)) {
-        feo_peer::BParts parts{};
-        parts.part[0] = static_cast<const float *>(B);
-        parts.world = 1;
-        parts.rows_per_part = (int)K;
-        feo_peer::XchgParams sync{};
-        sync.world = 1;  // epoch 0: no flags, no wait
-        return matmul_tf32x3_run(ctx, C, A, nullptr, &parts, &sync, M, K, N);
-    }
     return matmul_tf32x3_run(ctx, C, A, B, nullptr, nullptr, M, K, N);
 }
 

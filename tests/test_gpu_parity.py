@@ -801,14 +801,16 @@ def test_matmul_tf32x3_vs_oracle(feo, oracle):
 
 
 def test_matmul_tf32x3_kernel_variants(feo, oracle):
-    """The CTA-pair kernel (tcgen05 cta_group::2, persistent, run-time tile width BN) at every BN, the single-CTA kernel it
-    replaced (knob MATMUL_TF32_PAIR = 1), and the pre-pass overlapped with the main kernel (knob GATHER_OVERLAP = 2): each
-    inside the same f32 bound, on shapes that give a pair several tiles (persistence: barrier phases carry over), ragged
-    edges in M, N and K, an odd number of 128-row blocks (the odd CTA's rows fall outside M) and a single k-block."""
+    """The CTA-pair kernel (tcgen05 cta_group::2, persistent, run-time tile width BN) at every BN -- with B read as raw f32
+    tiles and split inside the kernel (MN-major operand; the default when N % 4 == 0) and with the split + transpose pre-pass
+    (knob MATMUL_TF32_BRAW = 1) -- and the single-CTA kernel it replaced (knob MATMUL_TF32_PAIR = 1): each inside the same
+    f32 bound and all bit-identical, on shapes that give a pair several tiles (persistence: barrier phases carry over),
+    ragged edges in M, N and K (N = 4 x odd: the last 32-column box of raw B overhangs; K % 32 != 0: TMA zero-fills the
+    missing k-rows), an odd number of 128-row blocks (the odd CTA's rows fall outside M) and a single k-block."""
     import feotensor_b200._lib as L
     ctx = feo.Context.default()
     rng = np.random.default_rng(701)
-    shapes = [(1024, 512, 8192 + 224), (2304, 160, 4000), (128, 64, 700), (385, 32, 257), (3000, 96, 3001), (640, 8192, 512)]
+    shapes = [(1024, 512, 8192 + 224), (2304, 160, 4000), (128, 64, 700), (385, 32, 257), (3000, 96, 3001), (640, 8192, 512), (515, 70, 1012)]
     try:
         for m, k, n in shapes:
             A, B = rand(oracle, rng, "f32", (m, k)), rand(oracle, rng, "f32", (k, n))
@@ -816,12 +818,12 @@ def test_matmul_tf32x3_kernel_variants(feo, oracle):
             exact = A.astype(np.float64) @ B.astype(np.float64)
             terms = np.abs(A.astype(np.float64)) @ np.abs(B.astype(np.float64))
             results = {}
-            for label, pair, bn, overlap in (("pair auto", 0, 0, 0), ("pair 256", 0, 256, 0), ("pair 224", 0, 224, 0), ("pair 192", 0, 192, 0),
-                                             ("pair 160", 0, 160, 0), ("pair 128", 0, 128, 0), ("pair 96", 0, 96, 0), ("pair 32", 0, 32, 0),
-                                             ("single", 1, 0, 0), ("pair overlap", 0, 0, 2), ("pair 224 overlap", 0, 224, 2), ("no overlap", 0, 0, 1)):
+            for label, pair, bn, braw in (("pair auto", 0, 0, 0), ("pair 256", 0, 256, 0), ("pair 224", 0, 224, 0), ("pair 192", 0, 192, 0),
+                                          ("pair 160", 0, 160, 0), ("pair 128", 0, 128, 0), ("pair 96", 0, 96, 0), ("pair 32", 0, 32, 0),
+                                          ("single", 1, 0, 0), ("pair prepass", 0, 0, 1), ("pair 224 prepass", 0, 224, 1), ("pair 96 prepass", 0, 96, 1)):
                 ctx.tune(L.KNOB_MATMUL_TF32_PAIR, pair)
                 ctx.tune(L.KNOB_MATMUL_TF32_BN, bn)
-                ctx.tune(L.KNOB_GATHER_OVERLAP, overlap)
+                ctx.tune(L.KNOB_MATMUL_TF32_BRAW, braw)
                 got = tA.matmul(tB, algo="tf32x3").to_numpy()
                 err = np.abs(got - exact)
                 assert np.all(err <= 2.0 ** -20 * terms), f"{label} {m}x{k}x{n}: max rel err {(err / terms).max():.3e} at {np.unravel_index(np.argmax(err / terms), err.shape)}"
@@ -832,7 +834,7 @@ def test_matmul_tf32x3_kernel_variants(feo, oracle):
     finally:
         ctx.tune(L.KNOB_MATMUL_TF32_PAIR, 0)
         ctx.tune(L.KNOB_MATMUL_TF32_BN, 0)
-        ctx.tune(L.KNOB_GATHER_OVERLAP, 0)
+        ctx.tune(L.KNOB_MATMUL_TF32_BRAW, 0)
 
 
 def test_pow_and_display(feo, kat, oracle):

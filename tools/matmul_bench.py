@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""3xTF32 matmul variants on one GPU: the CTA-pair kernel at several tile widths, the single-CTA kernel, pre-pass overlap.
+"""3xTF32 matmul variants on one GPU: the CTA-pair kernel (raw-B split in the kernel / pre-pass) at several tile widths and chunk lengths, the single-CTA kernel.
 
     python tools/matmul_bench.py [--shapes 8192x8192x8192,1024x8192x8192] [--iters 10]
 
@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--shapes", default="8192x8192x8192,1024x8192x8192,2048x8192x8192,4096x8192x8192")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--rounds", type=int, default=5)
-    ap.add_argument("--variants", default="pair,pair256,pair224,pair192,single,pair_overlap")
+    ap.add_argument("--variants", default="pair,pair_prepass,pair256,pair224,single")
     args = ap.parse_args()
     import torch
 
@@ -35,10 +35,12 @@ def main():
     torch.cuda.set_stream(torch.cuda.Stream())
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     vp = C.c_void_p
-    # name -> (MATMUL_TF32_PAIR, MATMUL_TF32_BN, GATHER_OVERLAP, MATMUL_TF32_KC)
+    # name -> (MATMUL_TF32_PAIR, MATMUL_TF32_BN, MATMUL_TF32_KC, MATMUL_TF32_BRAW)
     variants = {"pair": (0, 0, 0, 0), "pair256": (0, 256, 0, 0), "pair224": (0, 224, 0, 0), "pair192": (0, 192, 0, 0), "pair160": (0, 160, 0, 0),
-                "pair128": (0, 128, 0, 0), "single": (1, 0, 0, 0), "pair_overlap": (0, 0, 2, 0), "single_overlap": (1, 0, 2, 0),
-                "pair_kc1": (0, 0, 0, 1), "pair_kc4": (0, 0, 0, 4), "pair_kc8": (0, 0, 0, 8), "pair_kc256": (0, 0, 0, 256)}
+                "pair128": (0, 128, 0, 0), "single": (1, 0, 0, 0), "pair_kc1": (0, 0, 1, 0), "pair_kc3": (0, 0, 3, 0), "pair_kc4": (0, 0, 4, 0),
+                "pair_kc8": (0, 0, 8, 0), "pair_kc256": (0, 0, 256, 0),
+                # B split + transposed by a pre-pass (round-1 data path) instead of split from raw tiles inside the kernel
+                "pair_prepass": (0, 0, 0, 1), "pair_prepass256": (0, 256, 0, 1), "pair_prepass_kc4": (0, 0, 4, 1)}
     for shp in args.shapes.split(","):
         m, k, n = (int(x) for x in shp.split("x"))
         A = feo.Tensor.uniform(feo.shape(m, k), 40, dtype="f32", ctx=ctx)
@@ -55,10 +57,10 @@ def main():
         errs = {}
         for rnd in range(args.rounds):  # round-robin over the variants: clocks drift with temperature and the power cap
             for name in names:
-                pair, bn, ov, kc = variants[name]
+                pair, bn, kc, braw = variants[name]
+                ctx.tune(L.KNOB_MATMUL_TF32_BRAW, braw)
                 ctx.tune(L.KNOB_MATMUL_TF32_PAIR, pair)
                 ctx.tune(L.KNOB_MATMUL_TF32_BN, bn)
-                ctx.tune(L.KNOB_GATHER_OVERLAP, ov)
                 ctx.tune(L.KNOB_MATMUL_TF32_KC, kc)
                 fn = lambda: ctx.check(ctx.lib.feo_matmul(ctx.handle, L.MATMUL_TF32X3, L.F32, vp(Cm.data.ptr), vp(A.data.ptr), vp(B.data.ptr), m, k, n))
                 if rnd == 0:
@@ -82,8 +84,8 @@ def main():
         del A, B, Cm
     ctx.tune(L.KNOB_MATMUL_TF32_PAIR, 0)
     ctx.tune(L.KNOB_MATMUL_TF32_BN, 0)
-    ctx.tune(L.KNOB_GATHER_OVERLAP, 0)
     ctx.tune(L.KNOB_MATMUL_TF32_KC, 0)
+    ctx.tune(L.KNOB_MATMUL_TF32_BRAW, 0)
 
 
 if __name__ == "__main__":
