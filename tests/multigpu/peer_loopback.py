@@ -63,7 +63,8 @@ def main():
     # the 197 KB-shared-memory tensor-core kernel after small-carve-out kernels makes the SMs change their L1/shared split,
     # which did not happen while another rank's kernel was spinning -- an artefact of ranks sharing one GPU and process.)
     for dt, algo, (M, K, N) in (("i32", "simt", (8 * world, 16 * world, 24)), ("f64", "simt", (8 * world, 16 * world, 24)),
-                                ("f32", "tf32x3", (64 * world, 96 * world, 200)), ("f32", "tf32x3", (32 * world, 33 * world, 257))):
+                                ("f32", "tf32x3", (64 * world, 96 * world, 200)), ("f32", "tf32x3", (32 * world, 33 * world, 257)),
+                                ("f32", "tf32x3", (96 * world, 40 * world, 2084))):
         A, B = gen(dt, (M, K)), gen(dt, (K, N))
         kr = K // world
         ptrs = []

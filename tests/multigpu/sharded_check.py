@@ -158,8 +158,9 @@ def run_checks(feo, sharded, o, dist, ctx, eng, rank, world, label, with_gather=
                 np.testing.assert_allclose(r.local.to_numpy(), rows(w), rtol=1e-4, atol=1e-5)
             checks += 1
     if label == "peer":
-        # f32 on the tensor cores with the gather fused into the split / transpose pre-pass (ragged N and K included)
-        for (M, K, N) in ((64 * world, 96 * world, 200), (128 * world, 32 * world, 257)):
+        # f32 on the tensor cores, B's panels pulled from the peers while the matmul kernel runs: as raw rows when N % 4 == 0
+        # (split inside the kernel), fused into the split / transpose pre-pass otherwise (ragged N and K included)
+        for (M, K, N) in ((64 * world, 96 * world, 200), (128 * world, 32 * world, 257), (192 * world, 40 * world, 2084)):
             A, B = gen("f32", (M, K)), gen("f32", (K, N))
             Bsh = sharded.shard_rows(eng, B, peer=True)
             got = sharded.shard_rows(eng, A).matmul(Bsh, b_sharded=True, algo="tf32x3").local.to_numpy()
