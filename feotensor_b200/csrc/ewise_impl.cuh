@@ -333,11 +333,28 @@ int launch_tile(feo_ctx *ctx, T *out, const T *a, const T *b, BcastParams &P) {
     cfg.gridDim = dim3((unsigned)blocks);
     cfg.blockDim = dim3(kThreads);
     cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (ctx->l2_persist_bytes && ctx->l2_win_ptr && ctx->l2_win_bytes) {
+        // knob BCAST_L2KEEP = 2: the operand later launches read again (b of the config-2 slab loop) goes to the persisting
+        // carve-out, everything else streams
+        size_t bytes = ctx->l2_win_bytes;
+        if (bytes > ctx->l2_window_max) bytes = ctx->l2_window_max;
+        attr[na].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[na].val.accessPolicyWindow.base_ptr = const_cast<void *>(ctx->l2_win_ptr);
+        attr[na].val.accessPolicyWindow.num_bytes = bytes;
+        attr[na].val.accessPolicyWindow.hitRatio = bytes <= ctx->l2_persist_bytes ? 1.0f : (float)((double)ctx->l2_persist_bytes / (double)bytes);
+        attr[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = na;
     int *flag = ctx->arith_flag;
     const T *ca = a, *cb = b;
     FEO_CUDA(ctx, cudaLaunchKernelEx(&cfg, bcast_tile_kernel<T, OP, VB, PT, QT, A_QINV, B_PINV>, out, ca, cb, P, flag));
@@ -613,7 +630,19 @@ int broadcast_vec(feo_ctx *ctx, T *out, const T *a, const T *b, const Collapsed 
     P.tx = tx;
     P.ty = kThreads / tx;
     P.i_blocks = (P.ni_vec + tx - 1) / tx;
-    P.keep_operands = (ctx->knobs[FEO_KNOB_BCAST_L2KEEP] != 1);
+    P.keep_operands = (ctx->knobs[FEO_KNOB_BCAST_L2KEEP] == 0);
+    // the larger of the operands that do not move along some outer dim is the one worth keeping in L2 between launches
+    ctx->l2_win_ptr = nullptr;
+    ctx->l2_win_bytes = 0;
+    if (ctx->l2_persist_bytes) {
+        long long span_a = 1, span_b = 1;
+        for (int d = 0; d < c.rank; ++d) { span_a += (c.ext[d] - 1) * c.sa[d]; span_b += (c.ext[d] - 1) * c.sb[d]; }
+        const bool pick_b = (pd >= 0) && (qd < 0 || span_b >= span_a);
+        if (pd >= 0 || qd >= 0) {
+            ctx->l2_win_ptr = pick_b ? (const void *)b : (const void *)a;
+            ctx->l2_win_bytes = (size_t)(pick_b ? span_b : span_a) * sizeof(T);
+        }
+    }
 
     const bool both = pd >= 0 && qd >= 0;
     // Many short alternating axes ([16]^7 with a and b on alternate axes): the P x Q x inner tile is a few KiB and every CTA

@@ -188,6 +188,25 @@ int feo_tune(feo_ctx *ctx, int knob, int value) {
     if (!ctx || knob < 0 || knob >= FEO_KNOB_COUNT) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "unknown knob %d", knob);
     ctx->knobs[knob] = value;
     if (knob == FEO_KNOB_PEER_TIMEOUT_S) ctx->peer_timeout_ns = value > 0 ? (unsigned long long)value * 1000000000ull : 0;
+    if (knob == FEO_KNOB_BCAST_L2KEEP) {
+        // 2: reserve the largest persisting-L2 carve-out the device allows; broadcast launches then put an access-policy
+        // window on the operand that later launches re-read.  Anything else: give the carve-out back.
+        FEO_ENTER(ctx);
+        if (value >= 2) {  // 2: the largest carve-out the device allows; > 2: that many MiB
+            int max_persist = 0, max_window = 0;
+            FEO_CUDA(ctx, cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device));
+            FEO_CUDA(ctx, cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device));
+            if (value > 2 && ((size_t)value << 20) < (size_t)max_persist) max_persist = (int)((size_t)value << 20);
+            FEO_CUDA(ctx, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist));
+            ctx->l2_persist_bytes = (size_t)max_persist;
+            ctx->l2_window_max = (size_t)max_window;
+        } else if (ctx->l2_persist_bytes) {
+            FEO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            FEO_CUDA(ctx, cudaCtxResetPersistingL2Cache());
+            FEO_CUDA(ctx, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0));
+            ctx->l2_persist_bytes = 0;
+        }
+    }
     return FEO_OK;
 }
 

@@ -20,7 +20,8 @@ enum feo_knob {
     FEO_KNOB_MATMUL_TF32_KC = 3,  // k-blocks (of 32) per TMEM accumulation chunk in the 3xTF32 matmul (0 = default 2)
     FEO_KNOB_BCAST_LCHUNK = 4,  // rows of the loop dimension per thread in the hold+stream broadcast kernel (0 = auto)
     FEO_KNOB_PDL = 5,           // programmatic dependent launch of independent back-to-back broadcast kernels: 0 = on, 1 = off
-    FEO_KNOB_BCAST_L2KEEP = 6,  // L2 evict_last policy on broadcast operands: 0 = on, 1 = off
+    FEO_KNOB_BCAST_L2KEEP = 6,  // broadcast operands in L2: 0 = evict_last load policy, 1 = nothing, 2 = persisting access-policy window on the
+                                // operand that is re-read across launches (sets the device's persisting-L2 carve-out; 0 / 1 reset it)
     FEO_KNOB_REDUCE_FUSE = 7,   // split reductions: last-arriving CTA combines the partials in the same launch: 0 = auto (small inputs), 1 = off, 2 = always
     FEO_KNOB_GATHER_OVERLAP = 8,  // sharded-B matmul: pull B's panels on a side stream while the matmul kernel runs: 0 = on, 1 = off
     FEO_KNOB_MATMUL_SIMT = 9,   // SIMT matmul, aligned 4-byte types: 0 = auto (cp.async pipeline), 1 = register double buffering, 2..5 = pipeline variants
@@ -52,6 +53,10 @@ struct feo_ctx {
     unsigned int *counters = nullptr;   // zeroed arrival counters for the fused reduction combine
     size_t counters_len = 0;
     uint64_t launches = 0;
+    size_t l2_persist_bytes = 0;        // persisting-L2 carve-out set by knob BCAST_L2KEEP = 2 (0: none)
+    size_t l2_window_max = 0;           // cudaDevAttrMaxAccessPolicyWindowSize
+    const void *l2_win_ptr = nullptr;   // operand range of the launch being prepared that deserves the window
+    size_t l2_win_bytes = 0;
     int knobs[FEO_KNOB_COUNT] = {0};
     std::vector<feo_launch_rec> window;  // launches since the last fully serialising operation (see feo_pdl_admit)
     feo_launch_rec pending;              // ranges of the launch being prepared

@@ -983,6 +983,7 @@ template <typename T, int KIND, int MODE>
 __global__ void __launch_bounds__(kThreads) reduce_stage2_kernel(T *__restrict__ out, const void *__restrict__ partial,
                                                                  long long nout, long long S, int fin, T divisor, int *flag) {
     const Acc<T, KIND> *p = reinterpret_cast<const Acc<T, KIND> *>(partial);
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // stage 1 in front of this launch is complete and visible (no-op without PDL)
     if constexpr (MODE >= 1) {
         constexpr int LANES = MODE == 1 ? 32 : kThreads;
         const long long o = MODE == 1 ? ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5 : (long long)blockIdx.x;
@@ -1018,11 +1019,33 @@ __global__ void __launch_bounds__(kThreads) reduce_stage2_kernel(T *__restrict__
             }
         }
     } else {
-        const long long o = (long long)blockIdx.x * kThreads + threadIdx.x;
-        if (o >= nout) return;
-        Acc<T, KIND> acc = p[o];
-        for (long long s = 1; s < S; ++s) acc.merge(p[s * nout + o]);
-        finalize(acc, out, o, nout, fin, divisor, flag);
+        // Many outputs: four threads per output, each a contiguous run of splits fetched in batches of 8 (independent loads
+        // in flight), then a two-step shuffle tree.  (One thread per output with one load per merge was latency-bound: a
+        // 1 GiB block [2048,16384,8] reduced over [0,2] leaves 74 Welford partials for each of 16384 outputs, and their
+        // merge cost ~40 us of a 200 us call; neighbouring outputs still read neighbouring partials, so the loads coalesce.)
+        constexpr int Q = 4;
+        const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+        const long long o = t / Q;
+        const int g = (int)(t % Q);
+        const bool live = o < nout;  // whole quads are live or not (kThreads % Q == 0); dead lanes only take part in the shuffles
+        Acc<T, KIND> acc;
+        acc.init((T)0);
+        if constexpr (KIND == K_SQDEV) { if (live) acc.m = p[o].m; }
+        const long long per = (S + Q - 1) / Q;
+        const long long lo = g * per, hi = (lo + per < S) ? lo + per : S;
+        constexpr int B = 8;
+        for (long long s = lo; live && s < hi; s += B) {
+            Acc<T, KIND> buf[B];
+#pragma unroll
+            for (int i = 0; i < B; ++i)
+                if (s + i < hi) buf[i] = p[(s + i) * nout + o];
+#pragma unroll
+            for (int i = 0; i < B; ++i)
+                if (s + i < hi) acc.merge(buf[i]);
+        }
+#pragma unroll
+        for (int off = Q / 2; off > 0; off >>= 1) { const Acc<T, KIND> other = shfl_down_acc(acc, off); acc.merge(other); }
+        if (live && g == 0) finalize(acc, out, o, nout, fin, divisor, flag);
     }
 }
 
@@ -1243,14 +1266,26 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
     }
     FEO_LAUNCH_CHECK(ctx);
     if (G.S > 1 && !G.counters) {
+        // programmatic dependent launch: stage 2 is set up while stage 1 still runs and starts the moment it has finished
+        // (the kernel executes griddepcontrol.wait before it reads a partial)
+        auto stage2 = [&](auto kern, long long blocks) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)blocks);
+            cfg.blockDim = dim3(kThreads);
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = ctx->knobs[FEO_KNOB_PDL] == 1 ? 0 : 1;
+            return cudaLaunchKernelEx(&cfg, kern, out, (const void *)partial, (long long)G.nout, (long long)G.S, fin, divisor, flag);
+        };
         if (G.nout <= 64 && G.S >= 256) {
-            reduce_stage2_kernel<T, KIND, 2><<<(unsigned)G.nout, kThreads, 0, ctx->stream>>>(out, partial, G.nout, G.S, fin, divisor, flag);
+            FEO_CUDA(ctx, stage2(reduce_stage2_kernel<T, KIND, 2>, G.nout));
         } else if (G.nout < 4096) {
-            const long long blocks = feo_ceil_div((size_t)G.nout * 32, (size_t)kThreads);
-            reduce_stage2_kernel<T, KIND, 1><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, G.nout, G.S, fin, divisor, flag);
+            FEO_CUDA(ctx, stage2(reduce_stage2_kernel<T, KIND, 1>, (long long)feo_ceil_div((size_t)G.nout * 32, (size_t)kThreads)));
         } else {
-            const long long blocks = feo_ceil_div((size_t)G.nout, (size_t)kThreads);
-            reduce_stage2_kernel<T, KIND, 0><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, G.nout, G.S, fin, divisor, flag);
+            FEO_CUDA(ctx, stage2(reduce_stage2_kernel<T, KIND, 0>, (long long)feo_ceil_div((size_t)G.nout * 4, (size_t)kThreads)));  // four threads per output
         }
         FEO_LAUNCH_CHECK(ctx);
     }
