@@ -441,6 +441,22 @@ def run_suite(torch, feo, L, ctx, hbm_peak, tf_peak, device=0):
     tf32_yard = flop / timed(torch, lambda: torch.matmul(At, Bt), 5, 2) / 1e9
     torch.backends.cuda.matmul.allow_tf32 = old
     suite["C4_yardstick_cublas_tf32_1pass"] = {"TFLOP/s": round(tf32_yard, 1), "note": "library kernel, denominator for the TF32 pipe"}
+    # yardsticks for the FP32 SIMT pipe: cuBLAS SGEMM, and what FFMA2 sustains from registers alone (tools/ffma2_probe.cu,
+    # built by __graft_entry__.build(); no memory traffic at all) -- both land well under the nominal 74.4 TFLOP/s
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sgemm_yard = flop / timed(torch, lambda: torch.matmul(At, Bt), 2, 1) / 1e9
+    torch.backends.cuda.matmul.allow_tf32 = old
+    suite["C4_yardstick_cublas_sgemm"] = {"TFLOP/s": round(sgemm_yard, 1), "note": "library kernel, FP32 SIMT pipe"}
+    ffma2_yard = None
+    probe = os.path.join(ROOT, "build", "ffma2_probe")
+    if os.path.exists(probe):
+        try:
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device)))
+            lines = [json.loads(x) for x in subprocess.run([probe], capture_output=True, text=True, timeout=60, env=env).stdout.splitlines() if x.startswith("{")]
+            ffma2_yard = max(x["TFLOP/s"] for x in lines if x["probe"].startswith("ffma2"))
+            suite["C4_yardstick_ffma2_registers_only"] = {"TFLOP/s": ffma2_yard, "note": "fma.rn.f32x2 on the matmul's 8 x 4 accumulator-pair tile, operands in registers, no loads: the ceiling of the FP32 pipe as compiled code reaches it"}
+        except Exception as e:
+            suite["C4_yardstick_ffma2_registers_only"] = {"error": repr(e)}
     del At, Bt
     for algo in ("simt", "tf32x3"):
         rc = ctx.lib.feo_matmul(ctx.handle, L.ALGO_CODES[algo], L.F32, vp(Cm.data_ptr()), vp(A.data_ptr()), vp(B.data_ptr()), m, m, m)
@@ -455,9 +471,12 @@ def run_suite(torch, feo, L, ctx, hbm_peak, tf_peak, device=0):
             entry["tf32_pipe_TFLOP/s"] = round(3 * tf, 1)  # three TF32 MMAs per logical product
             entry["tf32_pipe_util_vs_cublas_tf32"] = round(3 * tf / tf32_yard, 3)
             entry["tf32_pipe_util_vs_bf16_peak_half"] = round(3 * tf / (tf_peak / 2), 3)
-            entry["includes"] = "hi/lo split pre-pass (2 launches) + tcgen05 kernel"
+            entry["includes"] = "hi/lo split pre-pass of A (1 launch) + tcgen05 CTA-pair kernel (B split from raw tiles inside it)"
         else:
             entry["frac_fp32_simt_peak_74.4"] = round(tf / 74.4, 3)
+            entry["frac_of_cublas_sgemm"] = round(tf / sgemm_yard, 3)
+            if ffma2_yard:
+                entry["frac_of_ffma2_register_probe"] = round(tf / ffma2_yard, 3)
         suite[f"C4_matmul_{algo}"] = entry
     del A, B, Cm
     torch.cuda.empty_cache()
@@ -813,6 +832,10 @@ def run_suite_sharded(torch, dist, feo, ctx, rank, world, hbm_peak, iters=10):
     return out
 
 
+def step_bytes_out_rank(nslabs, slab_elems):
+    return 4.0 * nslabs * slab_elems
+
+
 def bind_to_gpu_numa_node(torch, device):
     """Best effort: run this process on the CPUs of the NUMA node the GPU hangs off, so the pinned host buffers of the e2e
     leg are allocated there (8 ranks writing 55 GB/s each into one socket's memory is what limits e2e at N > 1).
@@ -942,47 +965,72 @@ def main():
     # ---- e2e: the same metric through the C ABI with HOST buffers (H2D + kernels + D2H in the timed region) ------
     e2e_steps = max(2, min(K, 3))
     numa_node = bind_to_gpu_numa_node(torch, local)
-    a_host = torch.from_numpy(a_h.reshape(-1).copy()).pin_memory()
-    b_host = torch.from_numpy(b_h.reshape(-1).copy()).pin_memory()
-    ring = [torch.empty(slab_elems, dtype=torch.float32).pin_memory() for _ in range(2)]
+    RING = 4  # pinned 1 GiB slots from the ABI's own allocator (feo_host_alloc); the copy stream walks them round robin
+
+    def host_buffer(nbytes):
+        p_ = vp()
+        ctx.check(lib.feo_host_alloc(h, nbytes, C.byref(p_)))
+        return p_.value
+
+    a_host, b_host = host_buffer(a.numel() * 4), host_buffer(b.numel() * 4)
+    C.memmove(a_host, a_h.ctypes.data, a.numel() * 4)
+    C.memmove(b_host, b_h.ctypes.data, b.numel() * 4)
+    ring = [host_buffer(4 * slab_elems) for _ in range(RING)]
     copy_stream = torch.cuda.Stream()
     main_stream = torch.cuda.current_stream()
     ctx_copy = feo.Context(local)  # second context on the copy stream: the D2H leg goes through the C ABI too
     ctx_copy.set_stream(copy_stream.cuda_stream)
 
     def e2e_step():
-        ctx.check(lib.feo_upload(h, vp(a.data_ptr()), vp(a_host.data_ptr()), a_host.numel() * 4))
-        ctx.check(lib.feo_upload(h, vp(b.data_ptr()), vp(b_host.data_ptr()), b_host.numel() * 4))
+        ctx.check(lib.feo_upload(h, vp(a.data_ptr()), vp(a_host), a.numel() * 4))
+        ctx.check(lib.feo_upload(h, vp(b.data_ptr()), vp(b_host), b.numel() * 4))
         for s in range(nslabs):
             ctx.check(lib.feo_ewise_broadcast(h, L.MUL, L.F32, vp(out.data_ptr() + 4 * s * slab_elems),
                                               vp(a.data_ptr() + 4 * s * SLAB_ROWS * D), vp(b.data_ptr()), 3, shape, sa, sb))
             ev = torch.cuda.Event()
             ev.record(main_stream)
             copy_stream.wait_event(ev)
-            ctx_copy.check(lib.feo_download_async(ctx_copy.handle, vp(ring[s % 2].data_ptr()), vp(out.data_ptr() + 4 * s * slab_elems),
-                                                  4 * slab_elems))
+            ctx_copy.check(lib.feo_download_async(ctx_copy.handle, vp(ring[s % RING]), vp(out.data_ptr() + 4 * s * slab_elems), 4 * slab_elems))
         main_stream.wait_stream(copy_stream)
 
-    e2e_step()
-    torch.cuda.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record()
-    torch.cuda.synchronize()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    def timed_max(fn, n):
+        fn()
+        torch.cuda.synchronize()
+        barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        t_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([t_ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+        return t_ms
+
+    e2e_ms = timed_max(e2e_step, e2e_steps)
     e2e_val = world * step_bytes_rank * e2e_steps / (e2e_ms * 1e-3) / 1e9
-    assert float(ring[(nslabs - 1) % 2][slab_elems - 1].item()) == float(out[nslabs * slab_elems - 1].item())
+    last = np.ctypeslib.as_array(C.cast(ring[(nslabs - 1) % RING], C.POINTER(C.c_float)), shape=(slab_elems,))
+    assert float(last[slab_elems - 1]) == float(out[nslabs * slab_elems - 1].item())
+
+    # What this box can move device -> host at all: every rank at once copies 1 GiB slabs of `out` into its pinned ring with
+    # plain cudaMemcpyAsync (torch's non-blocking copy), nothing else running.  e2e above is D2H-bound (32 GiB out per
+    # step against 75 MB in), so e2e / ceiling says how much of the platform's host path the pipeline uses.
+    ring_t = [torch.from_numpy(np.ctypeslib.as_array(C.cast(pz, C.POINTER(C.c_float)), shape=(slab_elems,))) for pz in ring]
+
+    def plain_d2h():
+        for s in range(nslabs):
+            ring_t[s % RING].copy_(out[s * slab_elems:(s + 1) * slab_elems], non_blocking=True)
+
+    ceil_ms = timed_max(plain_d2h, 1)
+    d2h_ceiling = world * step_bytes_out_rank(nslabs, slab_elems) / (ceil_ms * 1e-3) / 1e9
+    del ring_t, last
     ctx_copy.sync()
     ctx_copy.close()
-    del ring, a_host, b_host
+    for pz in ring + [a_host, b_host]:
+        ctx.check(lib.feo_host_free(h, vp(pz)))
 
     # ---- ncu-derived DRAM traffic of the dominant kernel (profiles/, per launch) if a capture was summarised ----
     traffic = None
@@ -1001,7 +1049,9 @@ def main():
                      "traffic": traffic, "kernel": "bcast_tile_kernel<float,MUL,16B,8,4>", "launch_ms": launch_ms, "peak_source": peak_src},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 4 * (ROWS_PER_RANK * D + D * D),
                 "d2h_bytes_per_step": 4 * ROWS_PER_RANK * D * D, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                "host_numa_node": numa_node},
+                "host_numa_node": numa_node, "ring_slots": RING, "ring_alloc": "feo_host_alloc",
+                "d2h_ceiling_gbs": d2h_ceiling, "frac_of_d2h_ceiling": (world * 4.0 * ROWS_PER_RANK * D * D * e2e_steps / (e2e_ms * 1e-3) / 1e9) / d2h_ceiling,
+                "ceiling_how": f"{world} rank(s) at once, plain cudaMemcpyAsync of the same 32 x 1 GiB slabs into the same pinned ring, max over ranks"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
 

@@ -173,7 +173,11 @@ __device__ __forceinline__ void fma2(unsigned long long &acc, unsigned long long
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
 }
 
-template <typename T, int STAGES, int KV, bool F2, int MINB = 2>
+// WL (warp layout): false = a warp is 2 x 16 threads of the 16 x 16 thread grid and a thread owns rows 4 ty .. 4 ty + 3 (+ 64);
+// true = a warp is 4 x 8 threads and a thread owns rows ty + 16 i: a warp's `a` access then touches four rows 80 bytes apart
+// (banks 0-3, 20-23, 8-11, 28-31) and its `b` access 128 contiguous bytes -- one shared-memory wavefront each, where the
+// 2 x 16 shape needs two for every `b` access (256 bytes): 4 instead of 6 wavefronts per 32 FFMA2.
+template <typename T, int STAGES, int KV, bool F2, int MINB = 2, bool WL = false>
 __global__ void __launch_bounds__(kThreads, MINB) matmul_simt_pipe_kernel(T *__restrict__ C, const T *__restrict__ A, const T *__restrict__ B,
                                                                         long long M, long long K, long long N) {
     static_assert(!F2 || std::is_same<T, float>::value, "FFMA2 is f32 only");
@@ -188,7 +192,9 @@ __global__ void __launch_bounds__(kThreads, MINB) matmul_simt_pipe_kernel(T *__r
     T *Bs = As + STAGES * BM * PAS;            // [STAGES][PBK][PBS]
 
     const int tid = threadIdx.x;
-    const int tx = tid % 16, ty = tid / 16;
+    const int tx = WL ? 8 * ((tid >> 5) & 1) + (tid & 7) : tid % 16;
+    const int ty = WL ? 4 * (tid >> 6) + ((tid >> 3) & 3) : tid / 16;
+    auto row_of = [&](int i) { return WL ? ty + 16 * i : (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4)); };  // i-th row of this thread's tile
     const long long m0 = (long long)blockIdx.y * BM, n0 = (long long)blockIdx.x * BN;
     // two 16-byte chunks of each panel per thread
     const T *Ag = A + (m0 + tid / 4) * K + (tid % 4) * VN;                  // rows tid/4 and 64 + tid/4, k-chunk tid%4
@@ -231,13 +237,13 @@ __global__ void __launch_bounds__(kThreads, MINB) matmul_simt_pipe_kernel(T *__r
             if (nx < nkt) issue(nx, ns);
             cp_async_commit();
         }
-        const T *as = As + stage * (BM * PAS) + (ty * 4) * PAS;
+        const T *as = As + stage * (BM * PAS);
         const T *bs = Bs + stage * (PBK * PBS) + tx * 4;
 #pragma unroll
         for (int kk = 0; kk < PBK; kk += KV) {
             KVec a[TM];
 #pragma unroll
-            for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const KVec *>(as + ((i < 4 ? i : 60 + i)) * PAS + kk);
+            for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const KVec *>(as + row_of(i) * PAS + kk);
 #pragma unroll
             for (int k = 0; k < KV; ++k) {
                 if constexpr (F2) {
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, MINB) matmul_simt_pipe_kernel(T *__r
 
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
-        const long long gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        const long long gm = m0 + row_of(i);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const long long gn = n0 + (h == 0 ? tx * 4 : 64 + tx * 4);
@@ -291,16 +297,16 @@ __global__ void __launch_bounds__(kThreads, MINB) matmul_simt_pipe_kernel(T *__r
     }
 }
 
-template <typename T, int STAGES, int KV, bool F2, int MINB = 2>
+template <typename T, int STAGES, int KV, bool F2, int MINB = 2, bool WL = false>
 int launch_pipe(feo_ctx *ctx, dim3 grid, T *C, const T *A, const T *B, size_t M, size_t K, size_t N) {
     static bool attr_set[64] = {false};  // the opt-in is per device (and per instantiation)
     const int dev = ctx->device & 63;
     constexpr int smem = pipe_smem_bytes<T, STAGES>();
     if (!attr_set[dev]) {
-        FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_simt_pipe_kernel<T, STAGES, KV, F2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_simt_pipe_kernel<T, STAGES, KV, F2, MINB, WL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set[dev] = true;
     }
-    matmul_simt_pipe_kernel<T, STAGES, KV, F2, MINB><<<grid, kThreads, smem, ctx->stream>>>(C, A, B, (long long)M, (long long)K, (long long)N);
+    matmul_simt_pipe_kernel<T, STAGES, KV, F2, MINB, WL><<<grid, kThreads, smem, ctx->stream>>>(C, A, B, (long long)M, (long long)K, (long long)N);
     FEO_LAUNCH_CHECK(ctx);
     return FEO_OK;
 }
@@ -325,6 +331,10 @@ int matmul_typed(feo_ctx *ctx, T *C, const T *A, const T *B, size_t M, size_t K,
                 case 4: return launch_pipe<T, 4, 2, kF>(ctx, grid, C, A, B, M, K, N);
                 case 5: return launch_pipe<T, 5, 4, kF>(ctx, grid, C, A, B, M, K, N);
                 case 6: return launch_pipe<T, 4, 4, kF, 1>(ctx, grid, C, A, B, M, K, N);
+                case 7: return launch_pipe<T, 4, 4, kF, 2, true>(ctx, grid, C, A, B, M, K, N);
+                case 8: return launch_pipe<T, 4, 2, kF, 2, true>(ctx, grid, C, A, B, M, K, N);
+                case 9: return launch_pipe<T, 4, 4, kF, 1, true>(ctx, grid, C, A, B, M, K, N);
+                case 10: return launch_pipe<T, 3, 4, kF, 2, true>(ctx, grid, C, A, B, M, K, N);
                 default: return launch_pipe<T, 4, 4, kF>(ctx, grid, C, A, B, M, K, N);
             }
         }
