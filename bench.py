@@ -869,6 +869,7 @@ def main():
     ap.add_argument("--ref-threads", type=int, default=1, help="--impl reference: host threads for the headline value (default 1 = the reference's stock single-threaded path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bcast-tile", type=int, default=0, help="FEO_KNOB_BCAST_TILE override (experiments)")
+    ap.add_argument("--prefetch", type=int, default=None, help="FEO_KNOB_BCAST_PREFETCH override (experiments): q-blocks ahead, 0 off")
     ap.add_argument("--l2keep", type=int, default=None, help="FEO_KNOB_BCAST_L2KEEP override (experiments): 0 evict_last loads, 1 nothing, 2 persisting window")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -901,6 +902,8 @@ def main():
         ctx.tune(L.KNOB_BCAST_TILE, args.bcast_tile)
     if args.l2keep is not None:
         ctx.tune(L.KNOB_BCAST_L2KEEP, args.l2keep)
+    if args.prefetch is not None:
+        ctx.tune(L.KNOB_BCAST_PREFETCH, args.prefetch)
     vp = C.c_void_p
     lib, h = ctx.lib, ctx.handle
 

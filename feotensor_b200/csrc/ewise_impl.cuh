@@ -94,6 +94,10 @@ struct BcastParams {
     int tx, ty;  // threads along inner vectors / along q tiles (tx * ty == kThreads)
     long long i_blocks, q_blocks, p_tiles;
     int keep_operands;  // 1: load operands with the L2 evict_last policy
+    // > 0: the CTAs of q-block bq also prefetch into L2 the rows of the P-invariant operand (b) that q-block bq + prefetch_q
+    // will load -- a large b is cold for every launch (the write stream of the previous one evicted it), and a CTA that has
+    // to wait for DRAM before its first store is ~10 % longer (measured: tools/slab_boundary.py)
+    int prefetch_q;
 };
 
 template <typename T, int VB> __device__ __forceinline__ AVec<T, VecW<T, VB>::value> load_operand(const T *p, int inner, unsigned long long pol = 0) {
@@ -143,6 +147,15 @@ __global__ void __launch_bounds__(kThreads) bcast_tile_kernel(T *__restrict__ ou
     // operands are re-read (by other CTAs now, by the next slab launch later) while the output streams through L2 once:
     // operands evict_last, output evict_first
     const unsigned long long pol = P.keep_operands ? l2_policy_evict_last() : 0ull;
+    if constexpr (B_PINV) {
+        // one lane per 128-byte line, first P tile only: fire-and-forget L2 prefetch of the b rows a later q-block needs
+        if (P.prefetch_q > 0 && bp == 0 && P.b_inner && (tx & (128 / VB - 1)) == 0) {
+            const long long qf = q0 + (long long)P.prefetch_q * P.ty * QT;
+#pragma unroll
+            for (int q = 0; q < QT; ++q)
+                if (qf + q < P.nq) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(b + ob + (qf + q) * P.sb_q));
+        }
+    }
 
     V va[A_QINV ? PT : PT * QT], vb[B_PINV ? QT : PT * QT];
 #pragma unroll
@@ -631,6 +644,13 @@ int broadcast_vec(feo_ctx *ctx, T *out, const T *a, const T *b, const Collapsed 
     P.ty = kThreads / tx;
     P.i_blocks = (P.ni_vec + tx - 1) / tx;
     P.keep_operands = (ctx->knobs[FEO_KNOB_BCAST_L2KEEP] == 0);
+    {
+        // L2 prefetch distance for the P-invariant operand, in q-blocks (knob BCAST_PREFETCH: 0 = off, n = distance).  Off by
+        // default: measured on the config-2 slab loop (profiles/r2_slab_loop.md) 128 q-blocks ahead gives +1 % (6508 -> 6577
+        // GB/s, inside the run-to-run spread), 512 ahead -3 % (the write stream evicts the lines before they are used).
+        const int kp = ctx->knobs[FEO_KNOB_BCAST_PREFETCH];
+        P.prefetch_q = (kp > 0 && pd >= 0 && qd >= 0) ? kp : 0;
+    }
     // the larger of the operands that do not move along some outer dim is the one worth keeping in L2 between launches
     ctx->l2_win_ptr = nullptr;
     ctx->l2_win_bytes = 0;

@@ -29,7 +29,8 @@ enum feo_knob {
     FEO_KNOB_MATMUL_TF32_PAIR = 11,  // 3xTF32 matmul: 0 = CTA-pair kernel (tcgen05 cta_group::2, persistent), 1 = one 128 x 256 tile per CTA
     FEO_KNOB_MATMUL_TF32_BN = 12,    // CTA-pair kernel: tile width (multiple of 32, <= 256); 0 = fewest waves x width
     FEO_KNOB_MATMUL_TF32_BRAW = 13,  // CTA-pair kernel: 0 = B read as raw f32 tiles and split hi/lo inside the kernel (needs N % 4 == 0), 1 = split + transpose pre-pass
-    FEO_KNOB_COUNT = 14
+    FEO_KNOB_BCAST_PREFETCH = 14,    // tiled broadcast kernel: L2 prefetch of the P-invariant operand, q-blocks ahead (0 = off)
+    FEO_KNOB_COUNT = 15
 };
 
 // Address ranges of a launch, for the hazard check that lets independent back-to-back kernels overlap their tails.
