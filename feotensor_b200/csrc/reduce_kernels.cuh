@@ -170,7 +170,11 @@ template <typename T> struct Acc<T, K_WELFORD> {
         if (on == (T)0) return;
         const T nn = n + on;
         const T d = omean - mean;
-        const T f = on / nn;
+        // equal counts (every level of a shuffle / shared-memory tree, equal splits, equal shards): on / nn is exactly 0.5, so
+        // the division -- a dozen instructions, and the bulk of a merge -- is skipped without changing a bit
+        T f;
+        if (on == n) f = (T)0.5;
+        else f = on / nn;
         mean += d * f;
         m2 += om2 + d * d * n * f;
         n = nn;
@@ -1167,7 +1171,10 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         G.lanes = (per_out >= 4096 && !many_outputs) ? kThreads : 32;
         const long long outs_per_block = kThreads / G.lanes;
         const long long base_blocks = feo_ceil_div((size_t)G.nout, (size_t)outs_per_block);
-        const long long want = 4 * target_blocks;  // several waves of small units: no ragged last wave
+        // several waves of small units: no ragged last wave.  Float variance: every block ends with a tree of Welford merges
+        // (shuffles + shared memory), ~12 % of a block that streams only 227 KiB (1 GiB over 4736 blocks: 172 us against
+        // 153 us for sum) -- so its blocks are four times longer
+        const long long want = (KIND == K_WELFORD ? 1 : 4) * target_blocks;
         long long S = forced > 0 ? forced : feo_ceil_div((size_t)want, (size_t)base_blocks);
         const long long min_elems = 4096;  // keep at least 16 KiB (f32) of work per split
         S = clampll(S, 1, per_out / min_elems > 0 ? per_out / min_elems : 1);
