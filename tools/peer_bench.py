@@ -40,6 +40,28 @@ def main():
     comm = sharded.PeerComm(ctx)
     engines = {"nccl": sharded.CudaEngine(ctx), "peer": sharded.CudaEngine(ctx, comm=comm)}
 
+    def nvlink_kib():
+        """(Tx, Rx) KiB summed over this GPU's NVLinks, from the driver's counters (`nvidia-smi nvlink -gt d`); None if unavailable."""
+        try:
+            import re
+            import subprocess
+            txt = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(local)], capture_output=True, text=True, timeout=20).stdout
+            tx = sum(int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", txt))
+            rx = sum(int(v) for v in re.findall(r"Data Rx:\s*(\d+)\s*KiB", txt))
+            return (tx, rx) if (tx or rx) else None
+        except Exception:
+            return None
+
+    def counted(fn):
+        """timed(fn) plus the NVLink bytes this rank moved per call (driver counters around warm-up + timed calls)."""
+        c0 = nvlink_kib()
+        us = timed(fn)
+        torch.cuda.synchronize()
+        c1 = nvlink_kib()
+        calls = 5 + args.iters
+        per = None if (c0 is None or c1 is None) else {"tx_MiB_per_call": round((c1[0] - c0[0]) / 1024 / calls, 2), "rx_MiB_per_call": round((c1[1] - c0[1]) / 1024 / calls, 2)}
+        return us, per
+
     def timed(fn):
         for _ in range(5):
             fn()
@@ -91,10 +113,16 @@ def main():
             def lean_peer():
                 lib.feo_reduce_sharded(comm.handle, kcode, code, C.c_void_p(out.data.ptr), C.c_void_p(x.data.ptr), len(ldims), shp, len(axes), ax,
                                        one.ctypes.data_as(C.c_void_p))
-            res["lean_nccl"], res["lean_peer"] = timed(lean_nccl), timed(lean_peer)
+            res["lean_nccl"] = timed(lean_nccl)
+            res["lean_peer"], nv = counted(lean_peer)
+            if nv:
+                nv["expected_rx_MiB"] = round((world - 1) * nout * np.dtype(x.dtype).itemsize / 2 ** 20, 2)
+                res_extra = {"nvlink_lean_peer": nv}
+            else:
+                res_extra = {}
         if rank == 0:
             print(json.dumps(dict({"case": name, "world": world, "local_dims": ldims, "speedup": round(res["nccl"] / res["peer"], 3)},
-                                  **{"us_" + k: round(v, 2) for k, v in res.items()})), flush=True)
+                                  **{"us_" + k: round(v, 2) for k, v in res.items()}, **(res_extra if kind in ("sum", "max") else {}))), flush=True)
         del x
     n_local = 1 << 20
     p = feo.Tensor.uniform(feo.Shape([n_local]), 1, dtype="f32", first_index=rank * n_local, ctx=ctx)
@@ -121,7 +149,10 @@ def main():
             sb = sharded.ShardedTensor(eng, Bl, [n, n], rank, world)
             if label == "peer":
                 sb.peer = buf
-            res[label] = timed(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
+            if label == "peer":
+                res[label], nv_mm = counted(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
+            else:
+                res[label] = timed(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
             if label == "peer":
                 ctx.tune(L.KNOB_GATHER_OVERLAP, 1)
                 res["peer_no_overlap"] = timed(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
@@ -133,7 +164,9 @@ def main():
             flop = 2.0 * n * n * n
             print(json.dumps(dict({"case": "c4_matmul_8192_b_sharded", "world": world, "speedup": round(res["nccl"] / res["peer"], 3),
                                    "tflops_peer_whole_job": round(flop / res["peer"] / 1e6, 1),
-                                   "tflops_nccl_whole_job": round(flop / res["nccl"] / 1e6, 1)},
+                                   "tflops_nccl_whole_job": round(flop / res["nccl"] / 1e6, 1),
+                                   "tflops_replicated_b_whole_job": round(flop / res["replicated_b"] / 1e6, 1),
+                                   "nvlink_peer": dict(nv_mm or {}, expected_rx_MiB=round((world - 1) * rows_ * n * 4 / 2 ** 20, 1))},
                                   **{"us_" + k: round(v, 1) for k, v in res.items()})), flush=True)
         dist.barrier()
         buf.close()
