@@ -48,8 +48,11 @@ int feo_side_stream(feo_ctx *ctx) {
     int lo = 0, hi = 0;
     FEO_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
     FEO_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
+    FEO_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_stream2, cudaStreamNonBlocking, hi));
     FEO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     FEO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    FEO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
+    FEO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_open, cudaEventDisableTiming));
     return FEO_OK;
 }
 
@@ -158,10 +161,14 @@ int feo_shutdown(feo_ctx *ctx) {
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->arith_flag) cudaFree(ctx->arith_flag);
     if (ctx->host_flags) cudaFreeHost(ctx->host_flags);
+    if (ctx->host_ones) cudaFreeHost(ctx->host_ones);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+    if (ctx->side_stream2) { cudaStreamSynchronize(ctx->side_stream2); cudaStreamDestroy(ctx->side_stream2); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
+    if (ctx->ev_open) cudaEventDestroy(ctx->ev_open);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return FEO_OK;

@@ -23,7 +23,9 @@ enum feo_knob {
     FEO_KNOB_BCAST_L2KEEP = 6,  // broadcast operands in L2: 0 = evict_last load policy, 1 = nothing, 2 = persisting access-policy window on the
                                 // operand that is re-read across launches (sets the device's persisting-L2 carve-out; 0 / 1 reset it)
     FEO_KNOB_REDUCE_FUSE = 7,   // split reductions: last-arriving CTA combines the partials in the same launch: 0 = auto (small inputs), 1 = off, 2 = always
-    FEO_KNOB_GATHER_OVERLAP = 8,  // sharded-B matmul: pull B's panels on a side stream while the matmul kernel runs: 0 = on, 1 = off
+    FEO_KNOB_GATHER_OVERLAP = 8,  // sharded-B matmul, how B's panels travel: 0 = auto (copy engines piecewise when every panel is whole k-blocks, else
+                                  // the matmul kernel pulls them itself), 1 = gather kernel in stream order, 2 = gather kernel on a side stream,
+                                  // 3 = copy engines, 4 = in-kernel pull (TMA bulk copies)
     FEO_KNOB_MATMUL_SIMT = 9,   // SIMT matmul, aligned 4-byte types: 0 = auto (cp.async pipeline), 1 = register double buffering, 2..5 = pipeline variants
     FEO_KNOB_PEER_TIMEOUT_S = 10,  // seconds a kernel waits for a peer before it raises the status flag and goes on (0 = for ever); default: FEO_PEER_TIMEOUT_S or 600
     FEO_KNOB_MATMUL_TF32_PAIR = 11,  // 3xTF32 matmul: 0 = CTA-pair kernel (tcgen05 cta_group::2, persistent), 1 = one 128 x 256 tile per CTA
@@ -43,12 +45,15 @@ struct feo_ctx {
     cudaStream_t stream = nullptr;      // stream in use
     cudaStream_t own_stream = nullptr;  // stream created by feo_init
     cudaStream_t side_stream = nullptr;  // high-priority helper stream (created on first use, see feo_side_stream)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side_stream2 = nullptr; // second helper stream: the copy-engine pull alternates its pieces between the two
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_open = nullptr;
     cudaMemPool_t pool = nullptr;       // this context's own stream-ordered pool (never trimmed at synchronisation)
     void *workspace = nullptr;          // scratch for two-stage reductions
     size_t workspace_bytes = 0;
     int *arith_flag = nullptr;          // device int, sticky
     int *host_flags = nullptr;          // pinned [2]: where feo_sync / feo_download read arith_flag and status_flag into
+    unsigned int *host_ones = nullptr;  // pinned array of ones (readiness flags published by H2D copies, see matmul_tf32x3.cu)
+    size_t host_ones_len = 0;
     int *status_flag = nullptr;         // device int, sticky: feo_peer::kStatusPeerTimeout (arith_flag + 1)
     unsigned long long peer_timeout_ns = 600ull * 1000000000ull;
     unsigned int *counters = nullptr;   // zeroed arrival counters for the fused reduction combine

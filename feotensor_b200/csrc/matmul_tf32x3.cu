@@ -415,14 +415,37 @@ struct PairArgs {
     int M, N, BN;               // BN: pair tile width (multiple of 32, <= 256)
     int num_k_blocks, kc;
     int tiles_m, tiles_n;       // pair tiles: ceil(M / 256), ceil(N / BN)
-    const unsigned int *ready;  // see matmul_tf32x3_kernel
+    const unsigned int *ready;  // see matmul_tf32x3_kernel; the counter of k-block kb is ready[kb >> ready_shift]
     unsigned int ready_need;
+    int ready_shift;
     int kb_rot;
     unsigned long long peer_timeout_ns;
     int *status;
+    // PULL: B's row panels live in peer memory; one thread per CTA copies them into the local raw B (pull_dst) with TMA bulk
+    // copies through two 16 KiB shared-memory slots, while the MMAs run on the panels already here
+    feo_peer::BParts parts;
+    feo_peer::XchgParams sync;
+    float *pull_dst;            // [K, N]
+    unsigned int *ready_w;      // the counters `ready` points at, writable
+    int K;
+    int own_kb;                 // > 0: the first own_kb k-block iterations are read straight from this rank's panel through map_b_lo
 };
 
-template <bool RAW_B>
+constexpr int P_PULL_CHUNK = 2048;                       // floats per bulk copy: 8 KiB of one row of B
+constexpr int P_PULL_SLOTS = 4;                          // ring of staging slots: two loads and up to two stores in flight
+constexpr int P_PULL_SMEM = P_PULL_SLOTS * P_PULL_CHUNK * 4;  // staged after the operand ring and the barriers
+
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *gdst, uint32_t smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+template <bool RAW_B, bool PULL = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 matmul_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                           const __grid_constant__ CUtensorMap map_b_hi /* RAW_B: the raw B[K,N] */, const __grid_constant__ CUtensorMap map_b_lo,
@@ -434,7 +457,9 @@ matmul_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
     uint64_t *raw_bar = empty_bar + P_STAGES;                                        // RAW_B: this CTA's raw-B bytes have landed
     uint64_t *tmem_full_bar = raw_bar + P_STAGES;                                    // [2], both CTAs (multicast commit)
     uint64_t *tmem_empty_bar = tmem_full_bar + 2;                                    // [2], used in the even CTA: 2 * kEpiWarps arrivals
-    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+    uint64_t *pull_bar = tmem_empty_bar + 2;                                         // [P_PULL_SLOTS], PULL: a peer chunk has landed
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(pull_bar + P_PULL_SLOTS);
+    uint8_t *pull_slots = smem + P_STAGES * P_STAGE + 256;                           // PULL: 2 x 16 KiB behind the barrier block
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta = cluster_ctarank();          // 0 = even CTA (issues the MMAs), 1 = odd
@@ -454,11 +479,12 @@ matmul_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
             mbar_init(&raw_bar[s], 1);
         }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 2 * kEpiWarps); }
+        for (int b = 0; b < P_PULL_SLOTS; ++b) mbar_init(&pull_bar[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
-        if (!RAW_B) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
     }
     if (warp == 1) {  // the same warp in both CTAs: one allocation of all 512 columns in both tensor memories
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(kTmemCols) : "memory");
@@ -487,7 +513,8 @@ matmul_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
             int tm, tn;
             tile_coords(t, tm, tn);
             const int m0 = tm * 2 * P_BM + (int)cta * P_BM, n0 = tn * BN + (int)cta * (BN / 2);
-            int ready_upto = args.ready ? 0 : num_k_blocks;
+            const int own_kb = RAW_B ? args.own_kb : 0;
+            int ready_upto = args.ready ? own_kb : num_k_blocks;
             for (int it = 0; it < num_k_blocks; ++it, ++g) {
                 if (it >= ready_upto) {
                     const unsigned long long t0 = feo_peer::global_ns();
@@ -497,7 +524,7 @@ matmul_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                             int kbl = it + lane + args.kb_rot;
                             if (kbl >= num_k_blocks) kbl -= num_k_blocks;
                             unsigned int v;
-                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(args.ready + kbl) : "memory");
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(args.ready + (kbl >> args.ready_shift)) : "memory");
                             ok = v >= args.ready_need;
                         }
                         const unsigned int mask = __ballot_sync(0xffffffffu, ok);
@@ -525,8 +552,13 @@ matmul_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                     tma_load_2d_pair(st + P_TILE_A, &map_a_lo, full_addr[s], kb * BK, m0);
                     if (RAW_B) {
                         mbar_expect_tx(&raw_bar[s], (uint32_t)nbox * P_BOX_BYTES);
+                        // this rank's own panel is read where it lies (map_b_lo, k relative to the panel); the rest from the
+                        // local raw B the pullers fill
+                        const bool own = it < own_kb;
+                        const CUtensorMap *bmap = own ? &map_b_lo : &map_b_hi;
+                        const int krow = own ? it * BK : kb * BK;
                         for (int i = 0; i < nbox; ++i)  // coordinates: (column, k-row) of B[K,N]
-                            tma_load_2d(st + 2 * P_TILE_A + i * P_BOX_BYTES, &map_b_hi, &raw_bar[s], n0 + i * P_BOX_N, kb * BK);
+                            tma_load_2d(st + 2 * P_TILE_A + i * P_BOX_BYTES, bmap, &raw_bar[s], n0 + i * P_BOX_N, krow);
                     } else {
                         tma_load_2d_pair(st + 2 * P_TILE_A, &map_b_hi, full_addr[s], kb * BK, n0);
                         tma_load_2d_pair(st + 2 * P_TILE_A + P_TILE_B, &map_b_lo, full_addr[s], kb * BK, n0);
@@ -536,7 +568,96 @@ matmul_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
             }
         }
     } else if (warp == 1) {
-        if (cta == 0 && lane == 0) {  // ===== MMA issuer: one thread of the even CTA, for the pair =====
+        if (PULL && lane == (cta == 0 ? 1 : 0)) {
+            // ===== puller: one otherwise idle thread per CTA (beside the MMA issuer in the even CTA: measured harmless) =====
+            // All-gather of B fused into the matmul kernel: the chunks of B[K,N] -- 16 KiB row segments, numbered in the rotated
+            // k order the MMAs walk (this rank's own panel first, then the peers' in ring order) -- are dealt round robin to the
+            // CTAs of the grid; each is copied peer memory -> shared memory -> local raw B with TMA bulk copies (no registers,
+            // a ring of four 8 KiB slots per CTA), and ready[k-block] counts the chunks that have landed.
+            const feo_peer::XchgParams &sy = args.sync;
+            if (sy.epoch != 0) {  // the peers' panels are complete: exchange number `epoch` (CTA 0 signals, every puller waits)
+                if (blockIdx.x == 0) {
+                    __threadfence_system();
+                    for (int r = 0; r < sy.world; ++r)
+                        feo_peer::st_release_sys(reinterpret_cast<unsigned long long *>(sy.win[r] + sy.rank * feo_peer::kFlagStride), sy.epoch);
+                }
+                const unsigned long long t0 = feo_peer::global_ns();
+                for (int r = 0; r < sy.world; ++r) {
+                    const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(sy.win[sy.rank] + r * feo_peer::kFlagStride);
+                    while (feo_peer::ld_acquire_sys(mine) < sy.epoch) {
+                        if (sy.timeout_ns != 0 && feo_peer::global_ns() - t0 > sy.timeout_ns) {
+                            if (sy.status && atomicOr(sy.status, feo_peer::kStatusPeerTimeout) == 0)
+                                printf("matmul_tf32x3: rank %d gave up waiting for rank %d's panel of B; result invalid\n", sy.rank, r);
+                            break;
+                        }
+                        __nanosleep(64);
+                    }
+                }
+            }
+            const int N = args.N, K = args.K;
+            const int segs = (N + P_PULL_CHUNK - 1) / P_PULL_CHUNK;          // chunks per row of B
+            // chunks in rotated order: (k-block iteration, row in block, segment); the first own_kb iterations are this rank's own
+            // panel, which the TMA producer reads where it lies (args.own_kb > 0), so they are not copied at all
+            const long long total = (long long)(num_k_blocks - args.own_kb) * BK * segs;
+            const long long first = blockIdx.x, stride = gridDim.x;
+            auto locate = [&](long long c, int &kb, const float *&src, float *&dst, uint32_t &bytes) {
+                const int seg = (int)(c % segs);
+                const long long rowi = c / segs;
+                int it = (int)(rowi / BK) + args.own_kb;
+                kb = it + args.kb_rot;
+                if (kb >= num_k_blocks) kb -= num_k_blocks;
+                const int k = kb * BK + (int)(rowi % BK);
+                const int n0 = seg * P_PULL_CHUNK;
+                const int len = (N - n0 < P_PULL_CHUNK) ? N - n0 : P_PULL_CHUNK;
+                bytes = k < K ? (uint32_t)len * 4u : 0u;                      // rows past K (padding of the last k-block): nothing to copy
+                const int r = k < K ? k / args.parts.rows_per_part : 0;
+                src = args.parts.part[r] + (size_t)(k - r * args.parts.rows_per_part) * N + n0;
+                dst = args.pull_dst + (size_t)k * N + n0;
+            };
+            constexpr int S = P_PULL_SLOTS, AHEAD = S - 2;
+            uint32_t phase = 0;                       // bit s: parity the next wait on pull_bar[s] uses
+            int ring_kb[S]; float *ring_dst[S]; uint32_t ring_bytes[S];
+            const long long n_my = first < total ? (total - first + stride - 1) / stride : 0;
+            auto issue = [&](long long j) {           // j-th of this CTA's chunks: peer memory -> slot j % S
+                const int sl = (int)(j % S);
+                const float *src;
+                locate(first + j * stride, ring_kb[sl], src, ring_dst[sl], ring_bytes[sl]);
+                if (ring_bytes[sl]) {
+                    mbar_expect_tx(&pull_bar[sl], ring_bytes[sl]);
+                    bulk_load(smem_u32(pull_slots + sl * (P_PULL_CHUNK * 4)), src, ring_bytes[sl], &pull_bar[sl]);
+                }
+            };
+            for (long long j = 0; j < AHEAD && j < n_my; ++j) issue(j);
+            int kb_prev = -1;                         // k-block of the chunk whose store may still be in flight
+            for (long long i = 0; i < n_my; ++i) {
+                const int sl = (int)(i % S);
+                if (i + AHEAD < n_my) {
+                    // slot (i + AHEAD) % S last held chunk i - 2: every store group but the newest has finished reading
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    issue(i + AHEAD);
+                }
+                const uint32_t bytes = ring_bytes[sl];
+                if (bytes) {
+                    mbar_wait(&pull_bar[sl], (phase >> sl) & 1u, 5, bar_limit);
+                    phase ^= 1u << sl;
+                    bulk_store(ring_dst[sl], smem_u32(pull_slots + sl * (P_PULL_CHUNK * 4)), bytes);
+                }
+                if (kb_prev >= 0) {  // the store before this one is complete (all groups but the newest): publish its chunk
+                    if (bytes) asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // no new group was committed above
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __threadfence();
+                    atomicAdd(args.ready_w + kb_prev, 1u);
+                }
+                kb_prev = ring_kb[sl];
+            }
+            if (kb_prev >= 0) {
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __threadfence();
+                atomicAdd(args.ready_w + kb_prev, 1u);
+            }
+        } else if (cta == 0 && lane == 0) {  // ===== MMA issuer: one thread of the even CTA, for the pair =====
             // kind::tf32, f32 accumulate, A K-major, B K-major (pre-split) or MN-major (RAW_B), M = 256 (the pair), N = BN
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (RAW_B ? (1u << 16) : 0u) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)((2 * P_BM) >> 4) << 24);
@@ -811,6 +932,9 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(float *__restrict__ br
     }
 }
 
+// Copy-engine route: the opening flag exchange (the peers' panels are complete) as a one-CTA kernel in front of the copies.
+__global__ void __launch_bounds__(32) pull_open_kernel(const __grid_constant__ feo_peer::XchgParams sync) { feo_peer::signal_and_wait(sync); }
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -824,6 +948,15 @@ EncodeTiledFn get_encode() {
             fn = reinterpret_cast<EncodeTiledFn>(p);
     }
     return fn;
+}
+
+typedef CUresult (*StreamWriteFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWriteFn get_stream_write() {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+        return reinterpret_cast<StreamWriteFn>(p);
+    return nullptr;
 }
 
 // 2-D row-major [rows, K] f32 tensor, box = BK x box_rows, 128-byte swizzle (16-byte atoms for K-major operands, 32-byte
@@ -865,6 +998,7 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
         FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_tf32x3_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
         FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_tf32x3_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+        FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_tf32x3_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM + P_PULL_SMEM));
         attr_set[dev] = true;
     }
     // workspace: A_hi | A_lo [M,Kp], then either Bt_hi | Bt_lo [N,Kp] (pre-pass) or, for RAW_B with a sharded B, the gathered
@@ -880,36 +1014,104 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
     const int num_kb = (int)(Kp / BK);
     static_assert(GT_K == BK, "one gather tile row = one k-block of the main kernel");
 
-    // B arriving from peers: the gather goes to a high-priority side stream and the main kernel consumes k-blocks as
-    // they are published (knob FEO_KNOB_GATHER_OVERLAP = 1: plain stream order instead)
+    // B arriving from peers, four routes (knob FEO_KNOB_GATHER_OVERLAP; measured in DESIGN.md 7.1):
+    //   copy engines (0 = auto when every panel is whole k-blocks, 3 = forced): peer cudaMemcpyAsync pieces into the local raw B
+    //       on two side streams, one readiness flag per piece; no SM is involved, so the pull proceeds at NVLink speed while
+    //       the persistent matmul kernel owns every SM.  This rank's own panel is read in place.
+    //   in-kernel pull (0 = auto otherwise, 4 = forced): one thread per CTA of the matmul kernel copies 8 KiB chunks peer memory
+    //       -> shared memory -> local raw B with TMA bulk copies (PULL) -- one launch does the all-gather and the product.
+    //   gather kernel on a high-priority side stream (2) / in plain stream order (1): round 1's scheme, and the only one for a
+    //       pre-split B (N % 4 != 0) or the single-CTA kernel.
     unsigned int *ready = nullptr;
     unsigned int ready_need = 0;
     int kb_rot = 0;
-    bool overlap = false;
+    bool overlap = false, two_streams = false, pull = false, own_direct = false;
+    int ready_shift = 0;  // one readiness counter per 2^ready_shift k-blocks (copy-engine route: one per piece)  // own_direct: this rank's panel is read in place (mb_lo), not copied
     if (parts) {
         kb_rot = (int)(((size_t)sync->rank * parts->rows_per_part) / BK);
-        overlap = ctx->knobs[FEO_KNOB_GATHER_OVERLAP] != 1 && feo_side_stream(ctx) == FEO_OK;
-        cudaStream_t gstream = ctx->stream;
-        if (overlap) {
+        const int kn = ctx->knobs[FEO_KNOB_GATHER_OVERLAP];
+        pull = raw_b && (kn == 4 || (kn == 0 && parts->rows_per_part % BK != 0));
+        // 3: the copy engines pull.  Each remote panel is cut into pieces of kPieceKb k-blocks; a piece is one peer
+        // cudaMemcpyAsync into the local raw B followed by a tiny host-to-device copy of ones onto its readiness counters -- both
+        // run on copy engines, so they make progress while the persistent matmul kernel owns every SM.  Needs whole k-blocks
+        // per panel (the own panel is then read in place through mb_lo and never copied).
+        const bool ce = raw_b && (kn == 3 || kn == 0) && parts->rows_per_part % BK == 0 && feo_side_stream(ctx) == FEO_OK;
+        if (ce) {
+            // Pieces of up to 32 k-blocks (32 MiB at N = 8192; a power of two that divides the panel), dealt alternately to two side
+            // streams, one readiness flag per piece written by cuStreamWriteValue32 (a front-end operation: no SM, no PCIe read).
+            // A stream operation costs several us whatever its size -- measured at 8 GPUs: 8 MiB pieces + host-to-device flag
+            // copies on one stream 1051 us for the whole call, 16 MiB pieces on two streams 748 us -- so pieces are large and the
+            // flag of one piece hides behind the transfer of the next.
+            int piece_kb = 1;
+            while (piece_kb < 32 && (parts->rows_per_part / BK) % (2 * piece_kb) == 0) piece_kb *= 2;
+            while ((1 << ready_shift) < piece_kb) ++ready_shift;
+            static StreamWriteFn write32 = get_stream_write();  // cleared for good the first time the driver refuses (e.g. for pool memory)
+            if (ctx->host_ones_len < (size_t)num_kb) {
+                if (ctx->host_ones) cudaFreeHost(ctx->host_ones);
+                ctx->host_ones = nullptr;
+                ctx->host_ones_len = 0;
+                FEO_CUDA(ctx, cudaMallocHost(&ctx->host_ones, (size_t)num_kb * sizeof(unsigned int)));
+                for (int i = 0; i < num_kb; ++i) ctx->host_ones[i] = 1u;
+                ctx->host_ones_len = (size_t)num_kb;
+            }
             ready = ready_ws;
+            ready_need = 1;
+            own_direct = true;
+            cudaStream_t ss[2] = {ctx->side_stream, ctx->side_stream2};
             FEO_CUDA(ctx, cudaMemsetAsync(ready, 0, (size_t)num_kb * sizeof(unsigned int), ctx->stream));
             FEO_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-            FEO_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
-            gstream = ctx->side_stream;
-        }
-        if (raw_b) {
-            const dim3 ggrid((unsigned)feo_ceil_div(N, (size_t)GR_COLS), (unsigned)num_kb);
-            ready_need = ggrid.x;
-            gather_rows_kernel<<<ggrid, 256, 0, gstream>>>(b_ws, *parts, *sync, (int)K, (int)N, kb_rot, ready);
+            FEO_CUDA(ctx, cudaStreamWaitEvent(ss[0], ctx->ev_fork, 0));
+            pull_open_kernel<<<1, 32, 0, ss[0]>>>(*sync);
+            FEO_LAUNCH_CHECK(ctx);
+            FEO_CUDA(ctx, cudaEventRecord(ctx->ev_open, ss[0]));
+            FEO_CUDA(ctx, cudaStreamWaitEvent(ss[1], ctx->ev_open, 0));
+            const int kb_per_part = parts->rows_per_part / BK;
+            int piece = 0;
+            for (int step = 1; step < parts->world; ++step) {  // ring order: every rank drains a different owner at any time
+                const int r = (sync->rank + step) % parts->world;
+                for (int kb0 = 0; kb0 < kb_per_part; kb0 += piece_kb, ++piece) {
+                    const size_t row0 = (size_t)r * parts->rows_per_part + (size_t)kb0 * BK;
+                    cudaStream_t st = ss[piece & 1];
+                    FEO_CUDA(ctx, cudaMemcpyAsync(b_ws + row0 * N, parts->part[r] + (size_t)kb0 * BK * N, (size_t)piece_kb * BK * N * sizeof(float),
+                                                  cudaMemcpyDeviceToDevice, st));
+                    unsigned int *flag = ready + ((row0 / BK) >> ready_shift);
+                    if (write32 && write32((CUstream)st, (CUdeviceptr)(uintptr_t)flag, 1u, 0) != CUDA_SUCCESS) write32 = nullptr;
+                    if (!write32) FEO_CUDA(ctx, cudaMemcpyAsync(flag, ctx->host_ones, sizeof(unsigned int), cudaMemcpyHostToDevice, st));
+                }
+            }
+            FEO_CUDA(ctx, cudaEventRecord(ctx->ev_join, ss[0]));
+            FEO_CUDA(ctx, cudaEventRecord(ctx->ev_join2, ss[1]));
+            overlap = true;   // join the side streams behind the matmul kernel
+            two_streams = true;
+        } else if (pull) {
+            ready = ready_ws;
+            ready_need = (unsigned)(BK * feo_ceil_div(N, (size_t)P_PULL_CHUNK));
+            own_direct = parts->rows_per_part % BK == 0;
+            FEO_CUDA(ctx, cudaMemsetAsync(ready, 0, (size_t)num_kb * sizeof(unsigned int), ctx->stream));
         } else {
-            bool vec = N % 4 == 0;
-            for (int r = 0; r < parts->world; ++r) vec = vec && feo_aligned16(parts->part[r]);
-            const dim3 ggrid((unsigned)feo_ceil_div(N, (size_t)GT_N), (unsigned)num_kb);
-            ready_need = ggrid.x;
-            split_transpose_gather_kernel<<<ggrid, 256, 0, gstream>>>(b_hi, b_lo, *parts, *sync, (int)K, (int)N, (int)Kp, vec, kb_rot, ready);
+            overlap = kn != 1 && feo_side_stream(ctx) == FEO_OK;
+            cudaStream_t gstream = ctx->stream;
+            if (overlap) {
+                ready = ready_ws;
+                FEO_CUDA(ctx, cudaMemsetAsync(ready, 0, (size_t)num_kb * sizeof(unsigned int), ctx->stream));
+                FEO_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+                FEO_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+                gstream = ctx->side_stream;
+            }
+            if (raw_b) {
+                const dim3 ggrid((unsigned)feo_ceil_div(N, (size_t)GR_COLS), (unsigned)num_kb);
+                ready_need = ggrid.x;
+                gather_rows_kernel<<<ggrid, 256, 0, gstream>>>(b_ws, *parts, *sync, (int)K, (int)N, kb_rot, ready);
+            } else {
+                bool vec = N % 4 == 0;
+                for (int r = 0; r < parts->world; ++r) vec = vec && feo_aligned16(parts->part[r]);
+                const dim3 ggrid((unsigned)feo_ceil_div(N, (size_t)GT_N), (unsigned)num_kb);
+                ready_need = ggrid.x;
+                split_transpose_gather_kernel<<<ggrid, 256, 0, gstream>>>(b_hi, b_lo, *parts, *sync, (int)K, (int)N, (int)Kp, vec, kb_rot, ready);
+            }
+            FEO_LAUNCH_CHECK(ctx);
+            if (overlap) FEO_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
         }
-        FEO_LAUNCH_CHECK(ctx);
-        if (overlap) FEO_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
     }
 
     size_t blocks = feo_ceil_div(a_elems / 4, (size_t)256);
@@ -946,6 +1148,9 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
             // B[K,N] (or its gathered copy) as it lies: inner dimension N, boxes of 32 columns x 32 k-rows; rows >= K read as zero
             ok = ok && make_map(&mb_hi, parts ? b_ws : (const float *)B, K, N, BK, true);
             mb_lo = mb_hi;
+            // PULL with whole k-blocks per panel: this rank's own panel is never copied, the kernel reads it through mb_lo
+            if (own_direct)
+                ok = ok && make_map(&mb_lo, parts->part[sync->rank], (size_t)parts->rows_per_part, N, BK, true);
         } else {
             ok = ok && make_map(&mb_hi, b_hi, N, Kp, bn / 2) && make_map(&mb_lo, b_lo, N, Kp, bn / 2);
         }
@@ -961,11 +1166,22 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
         pa.tiles_n = (int)tiles_n;
         pa.ready = ready;
         pa.ready_need = ready_need;
+        pa.ready_shift = ready_shift;
         pa.kb_rot = kb_rot;
         pa.peer_timeout_ns = ctx->peer_timeout_ns;
         pa.status = ctx->status_flag;
+        pa.own_kb = own_direct ? parts->rows_per_part / BK : 0;
+        if (pull) {
+            pa.parts = *parts;
+            pa.sync = *sync;
+            pa.pull_dst = b_ws;
+            pa.ready_w = ready;
+            pa.K = (int)K;
+        }
         const unsigned pairs = (unsigned)(tiles < (size_t)pairs_max ? tiles : (size_t)pairs_max);
-        if (raw_b)
+        if (pull)
+            matmul_tf32x3_pair_kernel<true, true><<<dim3(2 * pairs), P_THREADS, P_SMEM + P_PULL_SMEM, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pa);
+        else if (raw_b)
             matmul_tf32x3_pair_kernel<true><<<dim3(2 * pairs), P_THREADS, P_SMEM, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pa);
         else
             matmul_tf32x3_pair_kernel<false><<<dim3(2 * pairs), P_THREADS, P_SMEM, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pa);
@@ -982,6 +1198,7 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
         FEO_LAUNCH_CHECK(ctx);
     }
     if (overlap) FEO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // the workspace is reused by the next call
+    if (two_streams) FEO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));
     return FEO_OK;
 }
 

@@ -64,6 +64,7 @@ def main():
 
 
 def run_checks(feo, sharded, o, dist, ctx, eng, rank, world, label, with_gather=True):
+    import feotensor_b200._lib as L
     rng = np.random.default_rng(99)
     checks = 0
 
@@ -160,17 +161,29 @@ def run_checks(feo, sharded, o, dist, ctx, eng, rank, world, label, with_gather=
     if label == "peer":
         # f32 on the tensor cores, B's panels pulled from the peers while the matmul kernel runs: as raw rows when N % 4 == 0
         # (split inside the kernel), fused into the split / transpose pre-pass otherwise (ragged N and K included)
-        for (M, K, N) in ((64 * world, 96 * world, 200), (128 * world, 32 * world, 257), (192 * world, 40 * world, 2084)):
+        # Every way the panels can travel (knob GATHER_OVERLAP): 0 = auto, 3 = the copy engines pull them piecewise, 4 = the matmul
+        # kernel pulls them itself with TMA bulk copies, 2 / 1 = the gather kernel beside / in front of the matmul kernel -- same bits.
+        for (M, K, N) in ((64 * world, 96 * world, 200), (128 * world, 32 * world, 257), (192 * world, 40 * world, 2084), (256 * world, 512 * world, 4352)):
             A, B = gen("f32", (M, K)), gen("f32", (K, N))
             Bsh = sharded.shard_rows(eng, B, peer=True)
-            got = sharded.shard_rows(eng, A).matmul(Bsh, b_sharded=True, algo="tf32x3").local.to_numpy()
             exact = rows(A.astype(np.float64) @ B.astype(np.float64))
             bound = rows(np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64))
-            err = np.abs(got - exact)
-            assert np.all(err <= np.maximum(2 * np.abs(rows(o.matmul(A, B)) - exact), 2.0 ** -20 * bound)), f"tf32x3 sharded-B {M}x{K}x{N}"
+            ref_err = 2 * np.abs(rows(o.matmul(A, B)) - exact) if M * K * N <= 1 << 28 else 0.0
+            first = None
+            try:
+                for knob in (0, 3, 4, 2, 1):
+                    ctx.tune(L.KNOB_GATHER_OVERLAP, knob)
+                    got = sharded.shard_rows(eng, A).matmul(Bsh, b_sharded=True, algo="tf32x3").local.to_numpy()
+                    err = np.abs(got - exact)
+                    assert np.all(err <= np.maximum(ref_err, 2.0 ** -20 * bound)), f"tf32x3 sharded-B {M}x{K}x{N} knob {knob}"
+                    if first is None:
+                        first = got
+                    np.testing.assert_array_equal(got, first, err_msg=f"tf32x3 sharded-B {M}x{K}x{N}: knob {knob} differs from knob 0")
+                    checks += 1
+            finally:
+                ctx.tune(L.KNOB_GATHER_OVERLAP, 0)
             dist.barrier()
             Bsh.peer.close()
-            checks += 1
     return checks
 
 

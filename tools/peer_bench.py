@@ -153,9 +153,15 @@ def main():
                 res[label], nv_mm = counted(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
             else:
                 res[label] = timed(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
-            if label == "peer":
+            if label == "peer":  # default = auto (copy engines here); the other routes for comparison
+                ctx.tune(L.KNOB_GATHER_OVERLAP, 3)
+                res["peer_copy_engines"] = timed(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
+                ctx.tune(L.KNOB_GATHER_OVERLAP, 4)
+                res["peer_in_kernel_pull"] = timed(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
+                ctx.tune(L.KNOB_GATHER_OVERLAP, 2)
+                res["peer_gather_kernel_side_stream"] = timed(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
                 ctx.tune(L.KNOB_GATHER_OVERLAP, 1)
-                res["peer_no_overlap"] = timed(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
+                res["peer_gather_kernel_then_matmul"] = timed(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
                 ctx.tune(L.KNOB_GATHER_OVERLAP, 0)
         Bfull = feo.Tensor.uniform(feo.Shape([n, n]), 12, dtype="f32", ctx=ctx)
         sa = sharded.ShardedTensor(engines["nccl"], A, [n, n], rank, world)
