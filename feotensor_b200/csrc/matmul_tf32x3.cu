@@ -1037,13 +1037,14 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
         // per panel (the own panel is then read in place through mb_lo and never copied).
         const bool ce = raw_b && (kn == 3 || kn == 0) && parts->rows_per_part % BK == 0 && feo_side_stream(ctx) == FEO_OK;
         if (ce) {
-            // Pieces of up to 32 k-blocks (32 MiB at N = 8192; a power of two that divides the panel), dealt alternately to two side
-            // streams, one readiness flag per piece written by cuStreamWriteValue32 (a front-end operation: no SM, no PCIe read).
-            // A stream operation costs several us whatever its size -- measured at 8 GPUs: 8 MiB pieces + host-to-device flag
-            // copies on one stream 1051 us for the whole call, 16 MiB pieces on two streams 748 us -- so pieces are large and the
-            // flag of one piece hides behind the transfer of the next.
+            // Pieces of up to 16 k-blocks (16 MiB at N = 8192; a power of two that divides the panel), dealt alternately to two side
+            // streams, one readiness flag per piece (cuStreamWriteValue32 where the driver takes it for this memory, else a 4-byte
+            // host-to-device copy: both are front-end / copy-engine work, no SM).  A stream operation costs several us whatever
+            // its size and the consumer needs the pieces in order, so the piece size is a compromise -- measured at 8 GPUs
+            // (tools/peer_bench.py, whole call): 28 pieces on one stream 1051 us, 14 pieces on two streams 747 us, 7 pieces
+            // (whole panels) on two streams ~900 us (two panels share the ingress, the first one needed arrives late).
             int piece_kb = 1;
-            while (piece_kb < 32 && (parts->rows_per_part / BK) % (2 * piece_kb) == 0) piece_kb *= 2;
+            while (piece_kb < 16 && (parts->rows_per_part / BK) % (2 * piece_kb) == 0) piece_kb *= 2;
             while ((1 << ready_shift) < piece_kb) ++ready_shift;
             static StreamWriteFn write32 = get_stream_write();  // cleared for good the first time the driver refuses (e.g. for pool memory)
             if (ctx->host_ones_len < (size_t)num_kb) {

@@ -23,6 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--big", action="store_true", help="add the config-3 sized cases (1 GiB per rank)")
+    ap.add_argument("--only-matmul", action="store_true", help="skip the reductions and the dot: only the config-4 sharded-B matmul (implies --big)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -83,7 +84,9 @@ def main():
              ("c1_var_i32_[0,2]", "i32", [64, 128, 256], "var", [0, 2]),
              ("mid_sum_[0]", "f32", [8 * world, 16384, 8], "sum", [0]),
              ("mid_max_all", "f32", [8 * world, 16384, 8], "max", [0, 1, 2])]
-    if args.big:
+    if args.only_matmul:
+        args.big, cases = True, []
+    if args.big and not args.only_matmul:
         cases += [("c3_sum_[0]", "f32", [2048 * world, 16384, 8], "sum", [0]),
                   ("c3_var_[0]", "f32", [2048 * world, 16384, 8], "var", [0]),
                   ("c3_sum_[0,2]", "f32", [2048 * world, 16384, 8], "sum", [0, 2]),
@@ -124,7 +127,7 @@ def main():
             print(json.dumps(dict({"case": name, "world": world, "local_dims": ldims, "speedup": round(res["nccl"] / res["peer"], 3)},
                                   **{"us_" + k: round(v, 2) for k, v in res.items()}, **(res_extra if kind in ("sum", "max") else {}))), flush=True)
         del x
-    n_local = 1 << 20
+    n_local = 1 << 20 if not args.only_matmul else 1 << 10
     p = feo.Tensor.uniform(feo.Shape([n_local]), 1, dtype="f32", first_index=rank * n_local, ctx=ctx)
     q = feo.Tensor.uniform(feo.Shape([n_local]), 2, dtype="f32", first_index=rank * n_local, ctx=ctx)
     res = {}
@@ -144,7 +147,7 @@ def main():
         Bl = buf.tensor([rows_, n], "f32")
         ctx.check(ctx.lib.feo_fill_uniform(ctx.handle, Bl.data.code, C.c_void_p(Bl.data.ptr), rows_ * n, 12, rank * rows_ * n, -1.0, 1.0))
         res = {}
-        for label, eng in engines.items():
+        for label, eng in reversed(list(engines.items())):  # peer first: the library's routes before any NCCL all-gather of B ran
             sa = sharded.ShardedTensor(eng, A, [n, n], rank, world)
             sb = sharded.ShardedTensor(eng, Bl, [n, n], rank, world)
             if label == "peer":
