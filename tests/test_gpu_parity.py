@@ -837,6 +837,28 @@ def test_matmul_tf32x3_kernel_variants(feo, oracle):
         ctx.tune(L.KNOB_MATMUL_TF32_BRAW, 0)
 
 
+def test_broadcast_cache_policy_knobs_keep_the_bits(feo, oracle):
+    """The L2 policies of the tiled broadcast kernel are performance knobs only: evict_last hints (default), none, a
+    persisting access-policy window on the re-read operand, and the L2 prefetch of its rows for later CTAs must all give the
+    reference's bits (one IEEE multiply per element), on a shape where both operands are invariant somewhere (config 2's)
+    and with the prefetch distance larger and smaller than the number of q-blocks."""
+    import feotensor_b200._lib as L
+    ctx = feo.Context.default()
+    rng = np.random.default_rng(808)
+    a = rand(oracle, rng, "f32", (24, 1, 512))
+    b = rand(oracle, rng, "f32", (1, 700, 512))
+    ta, tb = feo.Tensor(feo.shape(24, 1, 512), a), feo.Tensor(feo.shape(1, 700, 512), b)
+    want = oracle.ewise_broadcast("mul", a, b)
+    try:
+        for l2keep, prefetch in ((0, 0), (1, 0), (2, 0), (16, 0), (0, 7), (0, 128), (0, 4096), (2, 64)):
+            ctx.tune(L.KNOB_BCAST_L2KEEP, l2keep)
+            ctx.tune(L.KNOB_BCAST_PREFETCH, prefetch)
+            np.testing.assert_array_equal(ta.broadcast("mul", tb).to_numpy(), want, err_msg=f"l2keep={l2keep} prefetch={prefetch}")
+    finally:
+        ctx.tune(L.KNOB_BCAST_L2KEEP, 0)
+        ctx.tune(L.KNOB_BCAST_PREFETCH, 0)
+
+
 def test_pow_and_display(feo, kat, oracle):
     """The section-8(f) rows: pow (tensor.rs:325-333; exact on the reference's own vectors, a few ulp elsewhere) and
     display (tensor.rs:507-551; host-side formatting)."""
