@@ -203,6 +203,24 @@ template <typename T> struct Acc<T, K_WELFORD> {
         if (n == (T)0) { n = (T)N; mean = bm; m2 = q; }  // first batch: nothing to merge, no division
         else merge_raw((T)N, bm, q);
     }
+    // The same with the merge weight f = N / (n + N) handed in: accumulators that advance in lock step (the W components of a
+    // column vector, the J columns of a thread) share one division per batch instead of doing one each.  Same bits.
+    template <int N> __device__ __forceinline__ void push_batch_f(const T (&x)[N], T f) {
+        T s = (T)0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) s += x[i];
+        const T bm = s * ((T)1 / (T)N);
+        T q = (T)0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { const T c = x[i] - bm; q += c * c; }
+        if (n == (T)0) { n = (T)N; mean = bm; m2 = q; }
+        else {
+            const T d = bm - mean;
+            mean += d * f;
+            m2 += q + d * d * n * f;
+            n += (T)N;
+        }
+    }
 };
 
 template <int KIND, typename T> __device__ __forceinline__ T aux_val(const T *aux, long long o) {
@@ -390,6 +408,12 @@ __global__ void __launch_bounds__(kThreads, (J > 1 && VEC && KIND == K_WELFORD) 
                     for (int k = 0; k < W; ++k) v[j][u].v[k] = w_mul(w, v[j][u].v[k]);
             }
         }
+        T wf = (T)0;  // Welford: every accumulator of this thread holds the same count, so one merge weight serves them all
+        if constexpr (KIND == K_WELFORD) {
+            const T n0 = acc[0][0].n;
+            if (n0 == (T)U) wf = (T)0.5;            // second batch: exactly one half, no division
+            else if (n0 != (T)0) wf = (T)U / (n0 + (T)U);
+        }
 #pragma unroll
         for (int j = 0; j < J; ++j)
             if (live[j]) {
@@ -398,7 +422,8 @@ __global__ void __launch_bounds__(kThreads, (J > 1 && VEC && KIND == K_WELFORD) 
                     T x[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) x[u] = v[j][u].v[k];
-                    acc[j][k].push_batch(x);
+                    if constexpr (KIND == K_WELFORD) acc[j][k].push_batch_f(x, wf);
+                    else acc[j][k].push_batch(x);
                 }
             }
     }
