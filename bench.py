@@ -818,7 +818,7 @@ def run_suite_sharded(torch, dist, feo, ctx, rank, world, hbm_peak, iters=10):
         par.expect(np.all(np.abs(got - exact) <= np.maximum(2 * np.abs(ref - exact), 2.0 ** -20 * terms)), f"matmul {label} vs f64")
         del Cl
         if label != "b_replicated":
-            entry["route"] = "B's row panels pulled from the peers by the copy engines in 32-k-block pieces while the matmul kernel runs (readiness flag per piece, own panel read in place)"
+            entry["route"] = "B's row panels pulled from the peers by the copy engines in 16-k-block pieces while the matmul kernel runs (readiness flag per piece, own panel read in place)"
             # the other routes of the library, same call (knob GATHER_OVERLAP): 4 = the matmul kernel pulls with TMA bulk copies, 2 = gather kernel on a side stream
             import feotensor_b200._lib as L_
             for knob, name in ((4, "ms_in_kernel_pull"), (2, "ms_gather_kernel_side_stream")):
