@@ -152,15 +152,15 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 // Panel geometry in bytes is the same for 4- and 8-byte elements: an A row is 64 bytes (four 16-byte chunks: 16 or 8
 // k-values), rows are padded by one chunk, and both panels are 512 chunks = two per thread.
-template <typename T> struct PipeGeom {
+template <typename T, int KM = 1> struct PipeGeom {
     static constexpr int VN = 16 / (int)sizeof(T);  // elements per 16-byte chunk
-    static constexpr int PBK = 4 * VN;              // k-panel depth: 16 (4-byte) or 8 (8-byte)
+    static constexpr int PBK = 4 * VN * KM;         // k-panel depth: 16 (4-byte) or 8 (8-byte), times KM
     static constexpr int PAS = PBK + VN;            // A panel row stride (elements): 80 bytes
     static constexpr int PBS = BN + VN;             // B panel row stride (elements)
     static constexpr int CPR = BN / VN;             // chunks per B row: 32 or 64
     static constexpr int stage_elems = BM * PAS + PBK * PBS;
 };
-template <typename T, int STAGES> constexpr int pipe_smem_bytes() { return STAGES * PipeGeom<T>::stage_elems * (int)sizeof(T); }
+template <typename T, int STAGES, int KM = 1> constexpr int pipe_smem_bytes() { return STAGES * PipeGeom<T, KM>::stage_elems * (int)sizeof(T); }
 
 // f32 only: two FMAs per instruction on 64-bit register pairs (FFMA2, new with sm_100).  Each lane is an IEEE fused
 // multiply-add, so results are bit-identical to fmaf; what changes is the issue rate and the register-file reads per FMA.
@@ -177,11 +177,13 @@ __device__ __forceinline__ void fma2(unsigned long long &acc, unsigned long long
 // true = a warp is 4 x 8 threads and a thread owns rows ty + 16 i: a warp's `a` access then touches four rows 80 bytes apart
 // (banks 0-3, 20-23, 8-11, 28-31) and its `b` access 128 contiguous bytes -- one shared-memory wavefront each, where the
 // 2 x 16 shape needs two for every `b` access (256 bytes): 4 instead of 6 wavefronts per 32 FFMA2.
-template <typename T, int STAGES, int KV, bool F2, int MINB = 2, bool WL = false>
+// KM: k-panel depth multiplier (KM = 2: 32 k-values per panel for 4-byte types, half as many CTA-wide barriers and cp.async
+// wait points per flop; three stages of 35 KiB then fill the shared memory of two CTAs per SM).
+template <typename T, int STAGES, int KV, bool F2, int MINB = 2, bool WL = false, int KM = 1>
 __global__ void __launch_bounds__(kThreads, MINB) matmul_simt_pipe_kernel(T *__restrict__ C, const T *__restrict__ A, const T *__restrict__ B,
                                                                         long long M, long long K, long long N) {
     static_assert(!F2 || std::is_same<T, float>::value, "FFMA2 is f32 only");
-    using PG = PipeGeom<T>;
+    using PG = PipeGeom<T, KM>;
     constexpr int VN = PG::VN, PBK = PG::PBK, PAS = PG::PAS, PBS = PG::PBS, CPR = PG::CPR;
     static_assert(PBK % KV == 0 && KV * sizeof(T) <= 16, "a is read in 16-byte (or narrower) k-vectors");
     using F = AVec<T, 4>;
@@ -196,18 +198,22 @@ __global__ void __launch_bounds__(kThreads, MINB) matmul_simt_pipe_kernel(T *__r
     const int ty = WL ? 4 * (tid >> 6) + ((tid >> 3) & 3) : tid / 16;
     auto row_of = [&](int i) { return WL ? ty + 16 * i : (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4)); };  // i-th row of this thread's tile
     const long long m0 = (long long)blockIdx.y * BM, n0 = (long long)blockIdx.x * BN;
-    // two 16-byte chunks of each panel per thread
-    const T *Ag = A + (m0 + tid / 4) * K + (tid % 4) * VN;                  // rows tid/4 and 64 + tid/4, k-chunk tid%4
-    const T *Bg = B + (long long)(tid / CPR) * N + n0 + (tid % CPR) * VN;   // k-rows tid/CPR and PBK/2 + tid/CPR
-    T *a_dst = As + (tid / 4) * PAS + (tid % 4) * VN;
-    T *b_dst = Bs + (tid / CPR) * PBS + (tid % CPR) * VN;
+    // 2 * KM 16-byte chunks of each panel per thread: chunk c = tid + 256 i is (row c / ACH, k-chunk c % ACH) of the A panel
+    // and (k-row c / CPR, column chunk c % CPR) of the B panel
+    constexpr int ACH = PBK / VN;  // chunks per A row: 4 * KM
     auto issue = [&](long long kt, int stage) {
-        T *ad = a_dst + stage * (BM * PAS), *bd = b_dst + stage * (PBK * PBS);
-        const T *ag = Ag + kt * PBK, *bg = Bg + kt * PBK * N;
-        cp_async16(ad, ag);
-        cp_async16(ad + 64 * PAS, ag + 64 * K);
-        cp_async16(bd, bg);
-        cp_async16(bd + (PBK / 2) * PBS, bg + (PBK / 2) * N);
+        T *ad = As + stage * (BM * PAS), *bd = Bs + stage * (PBK * PBS);
+        const T *ag = A + m0 * K + kt * PBK, *bg = B + kt * PBK * N + n0;
+#pragma unroll
+        for (int i = 0; i < 2 * KM; ++i) {
+            const int c = tid + i * kThreads;
+            cp_async16(ad + (c / ACH) * PAS + (c % ACH) * VN, ag + (long long)(c / ACH) * K + (c % ACH) * VN);
+        }
+#pragma unroll
+        for (int i = 0; i < 2 * KM; ++i) {
+            const int c = tid + i * kThreads;
+            cp_async16(bd + (c / CPR) * PBS + (c % CPR) * VN, bg + (long long)(c / CPR) * N + (c % CPR) * VN);
+        }
     };
 
     T acc[TM][TN];
@@ -297,16 +303,16 @@ __global__ void __launch_bounds__(kThreads, MINB) matmul_simt_pipe_kernel(T *__r
     }
 }
 
-template <typename T, int STAGES, int KV, bool F2, int MINB = 2, bool WL = false>
+template <typename T, int STAGES, int KV, bool F2, int MINB = 2, bool WL = false, int KM = 1>
 int launch_pipe(feo_ctx *ctx, dim3 grid, T *C, const T *A, const T *B, size_t M, size_t K, size_t N) {
     static bool attr_set[64] = {false};  // the opt-in is per device (and per instantiation)
     const int dev = ctx->device & 63;
-    constexpr int smem = pipe_smem_bytes<T, STAGES>();
+    constexpr int smem = pipe_smem_bytes<T, STAGES, KM>();
     if (!attr_set[dev]) {
-        FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_simt_pipe_kernel<T, STAGES, KV, F2, MINB, WL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        FEO_CUDA(ctx, cudaFuncSetAttribute(matmul_simt_pipe_kernel<T, STAGES, KV, F2, MINB, WL, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set[dev] = true;
     }
-    matmul_simt_pipe_kernel<T, STAGES, KV, F2, MINB, WL><<<grid, kThreads, smem, ctx->stream>>>(C, A, B, (long long)M, (long long)K, (long long)N);
+    matmul_simt_pipe_kernel<T, STAGES, KV, F2, MINB, WL, KM><<<grid, kThreads, smem, ctx->stream>>>(C, A, B, (long long)M, (long long)K, (long long)N);
     FEO_LAUNCH_CHECK(ctx);
     return FEO_OK;
 }
@@ -335,6 +341,8 @@ int matmul_typed(feo_ctx *ctx, T *C, const T *A, const T *B, size_t M, size_t K,
                 case 8: return launch_pipe<T, 4, 2, kF, 2, true>(ctx, grid, C, A, B, M, K, N);
                 case 9: return launch_pipe<T, 4, 4, kF, 1, true>(ctx, grid, C, A, B, M, K, N);
                 case 10: return launch_pipe<T, 3, 4, kF, 2, true>(ctx, grid, C, A, B, M, K, N);
+                case 11: if (K % 32 == 0) return launch_pipe<T, 3, 4, kF, 2, false, 2>(ctx, grid, C, A, B, M, K, N); break;
+                case 12: if (K % 32 == 0) return launch_pipe<T, 3, 4, kF, 2, true, 2>(ctx, grid, C, A, B, M, K, N); break;
                 default: return launch_pipe<T, 4, 4, kF>(ctx, grid, C, A, B, M, K, N);
             }
         }
