@@ -26,7 +26,7 @@ enum feo_knob {
     FEO_KNOB_GATHER_OVERLAP = 8,  // sharded-B matmul, how B's panels travel: 0 = auto (copy engines piecewise when every panel is whole k-blocks, else
                                   // the matmul kernel pulls them itself), 1 = gather kernel in stream order, 2 = gather kernel on a side stream,
                                   // 3 = copy engines, 4 = in-kernel pull (TMA bulk copies)
-    FEO_KNOB_MATMUL_SIMT = 9,   // SIMT matmul, aligned 4-byte types: 0 = auto (cp.async pipeline), 1 = register double buffering, 2..5 = pipeline variants
+    FEO_KNOB_MATMUL_SIMT = 9,   // SIMT matmul, aligned 4-byte types: 0 = auto (cp.async pipeline), 1 = register double buffering, 2..13 = pipeline variants (matmul_simt.cu)
     FEO_KNOB_PEER_TIMEOUT_S = 10,  // seconds a kernel waits for a peer before it raises the status flag and goes on (0 = for ever); default: FEO_PEER_TIMEOUT_S or 600
     FEO_KNOB_MATMUL_TF32_PAIR = 11,  // 3xTF32 matmul: 0 = CTA-pair kernel (tcgen05 cta_group::2, persistent), 1 = one 128 x 256 tile per CTA
     FEO_KNOB_MATMUL_TF32_BN = 12,    // CTA-pair kernel: tile width (multiple of 32, <= 256); 0 = fewest waves x width

@@ -744,7 +744,7 @@ def test_matmul_simt_pipeline_variants_agree(feo, oracle):
                 base = ta.matmul(tb, algo="simt").to_numpy()
                 if dt in INTS:
                     np.testing.assert_array_equal(base, oracle.matmul(A, B), err_msg=f"{dt} {m}x{k}x{n}")
-                for v in (0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12):
+                for v in (0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13):
                     ctx.tune(L.KNOB_MATMUL_SIMT, v)
                     np.testing.assert_array_equal(ta.matmul(tb, algo="simt").to_numpy(), base, err_msg=f"{dt} {m}x{k}x{n} variant {v}")
     finally:
