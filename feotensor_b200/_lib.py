@@ -18,7 +18,7 @@ F32, F64, I32, I64, U32 = 0, 1, 2, 3, 4
 ADD, SUB, MUL, DIV = 0, 1, 2, 3
 SUM, MEAN, VAR, MAX, MIN = 0, 1, 2, 3, 4
 MATMUL_AUTO, MATMUL_SIMT, MATMUL_TF32X3 = 0, 1, 2
-KNOB_BCAST_TILE, KNOB_REDUCE_SPLIT, KNOB_REDUCE_BLOCKS_PER_SM, KNOB_MATMUL_TF32_KC, KNOB_BCAST_LCHUNK, KNOB_PDL, KNOB_BCAST_L2KEEP, KNOB_REDUCE_FUSE, KNOB_GATHER_OVERLAP, KNOB_MATMUL_SIMT, KNOB_PEER_TIMEOUT_S, KNOB_MATMUL_TF32_PAIR, KNOB_MATMUL_TF32_BN, KNOB_MATMUL_TF32_BRAW, KNOB_BCAST_PREFETCH = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14
+KNOB_BCAST_TILE, KNOB_REDUCE_SPLIT, KNOB_REDUCE_BLOCKS_PER_SM, KNOB_MATMUL_TF32_KC, KNOB_BCAST_LCHUNK, KNOB_PDL, KNOB_BCAST_L2KEEP, KNOB_REDUCE_FUSE, KNOB_GATHER_OVERLAP, KNOB_MATMUL_SIMT, KNOB_PEER_TIMEOUT_S, KNOB_MATMUL_TF32_PAIR, KNOB_MATMUL_TF32_BN, KNOB_MATMUL_TF32_BRAW, KNOB_BCAST_PREFETCH, KNOB_PULL_SHAPE = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15
 MAX_RANK = 8
 
 DTYPE_CODES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32,

@@ -48,10 +48,12 @@ int feo_side_stream(feo_ctx *ctx) {
     int lo = 0, hi = 0;
     FEO_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
     FEO_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
-    FEO_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_stream2, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 3; ++i) {
+        FEO_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->pull_streams[i], cudaStreamNonBlocking, hi));
+        FEO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pull_joins[i], cudaEventDisableTiming));
+    }
     FEO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     FEO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-    FEO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
     FEO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_open, cudaEventDisableTiming));
     return FEO_OK;
 }
@@ -164,10 +166,12 @@ int feo_shutdown(feo_ctx *ctx) {
     if (ctx->host_ones) cudaFreeHost(ctx->host_ones);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
-    if (ctx->side_stream2) { cudaStreamSynchronize(ctx->side_stream2); cudaStreamDestroy(ctx->side_stream2); }
+    for (int i = 0; i < 3; ++i) {
+        if (ctx->pull_streams[i]) { cudaStreamSynchronize(ctx->pull_streams[i]); cudaStreamDestroy(ctx->pull_streams[i]); }
+        if (ctx->pull_joins[i]) cudaEventDestroy(ctx->pull_joins[i]);
+    }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->ev_open) cudaEventDestroy(ctx->ev_open);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;

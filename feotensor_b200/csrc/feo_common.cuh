@@ -32,7 +32,8 @@ enum feo_knob {
     FEO_KNOB_MATMUL_TF32_BN = 12,    // CTA-pair kernel: tile width (multiple of 32, <= 256); 0 = fewest waves x width
     FEO_KNOB_MATMUL_TF32_BRAW = 13,  // CTA-pair kernel: 0 = B read as raw f32 tiles and split hi/lo inside the kernel (needs N % 4 == 0), 1 = split + transpose pre-pass
     FEO_KNOB_BCAST_PREFETCH = 14,    // tiled broadcast kernel: L2 prefetch of the P-invariant operand, q-blocks ahead (0 = off)
-    FEO_KNOB_COUNT = 15
+    FEO_KNOB_PULL_SHAPE = 15,        // copy-engine route of the sharded-B matmul: 100 * streams (1..4) + k-blocks per piece (power of two); 0 = 2 streams x 16
+    FEO_KNOB_COUNT = 16
 };
 
 // Address ranges of a launch, for the hazard check that lets independent back-to-back kernels overlap their tails.
@@ -45,8 +46,9 @@ struct feo_ctx {
     cudaStream_t stream = nullptr;      // stream in use
     cudaStream_t own_stream = nullptr;  // stream created by feo_init
     cudaStream_t side_stream = nullptr;  // high-priority helper stream (created on first use, see feo_side_stream)
-    cudaStream_t side_stream2 = nullptr; // second helper stream: the copy-engine pull alternates its pieces between the two
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_open = nullptr;
+    cudaStream_t pull_streams[3] = {nullptr, nullptr, nullptr};  // further helper streams: the copy-engine pull deals its pieces over side_stream and these
+    cudaEvent_t pull_joins[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_open = nullptr;
     cudaMemPool_t pool = nullptr;       // this context's own stream-ordered pool (never trimmed at synchronisation)
     void *workspace = nullptr;          // scratch for two-stage reductions
     size_t workspace_bytes = 0;

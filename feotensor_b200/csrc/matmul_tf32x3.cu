@@ -1025,7 +1025,8 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
     unsigned int *ready = nullptr;
     unsigned int ready_need = 0;
     int kb_rot = 0;
-    bool overlap = false, two_streams = false, pull = false, own_direct = false;
+    bool overlap = false, pull = false, own_direct = false;
+    int n_streams = 1;    // copy-engine route: side streams in use (their join events are waited for behind the matmul kernel)
     int ready_shift = 0;  // one readiness counter per 2^ready_shift k-blocks (copy-engine route: one per piece)  // own_direct: this rank's panel is read in place (mb_lo), not copied
     if (parts) {
         kb_rot = (int)(((size_t)sync->rank * parts->rows_per_part) / BK);
@@ -1043,8 +1044,14 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
             // its size and the consumer needs the pieces in order, so the piece size is a compromise -- measured at 8 GPUs
             // (tools/peer_bench.py, whole call): 28 pieces on one stream 1051 us, 14 pieces on two streams 747 us, 7 pieces
             // (whole panels) on two streams ~900 us (two panels share the ingress, the first one needed arrives late).
+            int piece_max = 16;
+            n_streams = 2;
+            if (const int shape = ctx->knobs[FEO_KNOB_PULL_SHAPE]; shape > 0) {  // experiments: 100 * streams + k-blocks per piece
+                n_streams = shape / 100 < 1 ? 1 : (shape / 100 > 4 ? 4 : shape / 100);
+                piece_max = shape % 100 > 0 ? shape % 100 : 16;
+            }
             int piece_kb = 1;
-            while (piece_kb < 16 && (parts->rows_per_part / BK) % (2 * piece_kb) == 0) piece_kb *= 2;
+            while (2 * piece_kb <= piece_max && (parts->rows_per_part / BK) % (2 * piece_kb) == 0) piece_kb *= 2;
             while ((1 << ready_shift) < piece_kb) ++ready_shift;
             static StreamWriteFn write32 = get_stream_write();  // cleared for good the first time the driver refuses (e.g. for pool memory)
             if (ctx->host_ones_len < (size_t)num_kb) {
@@ -1058,21 +1065,21 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
             ready = ready_ws;
             ready_need = 1;
             own_direct = true;
-            cudaStream_t ss[2] = {ctx->side_stream, ctx->side_stream2};
+            cudaStream_t ss[4] = {ctx->side_stream, ctx->pull_streams[0], ctx->pull_streams[1], ctx->pull_streams[2]};
             FEO_CUDA(ctx, cudaMemsetAsync(ready, 0, (size_t)num_kb * sizeof(unsigned int), ctx->stream));
             FEO_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
             FEO_CUDA(ctx, cudaStreamWaitEvent(ss[0], ctx->ev_fork, 0));
             pull_open_kernel<<<1, 32, 0, ss[0]>>>(*sync);
             FEO_LAUNCH_CHECK(ctx);
             FEO_CUDA(ctx, cudaEventRecord(ctx->ev_open, ss[0]));
-            FEO_CUDA(ctx, cudaStreamWaitEvent(ss[1], ctx->ev_open, 0));
+            for (int i = 1; i < n_streams; ++i) FEO_CUDA(ctx, cudaStreamWaitEvent(ss[i], ctx->ev_open, 0));
             const int kb_per_part = parts->rows_per_part / BK;
             int piece = 0;
             for (int step = 1; step < parts->world; ++step) {  // ring order: every rank drains a different owner at any time
                 const int r = (sync->rank + step) % parts->world;
                 for (int kb0 = 0; kb0 < kb_per_part; kb0 += piece_kb, ++piece) {
                     const size_t row0 = (size_t)r * parts->rows_per_part + (size_t)kb0 * BK;
-                    cudaStream_t st = ss[piece & 1];
+                    cudaStream_t st = ss[piece % n_streams];
                     FEO_CUDA(ctx, cudaMemcpyAsync(b_ws + row0 * N, parts->part[r] + (size_t)kb0 * BK * N, (size_t)piece_kb * BK * N * sizeof(float),
                                                   cudaMemcpyDeviceToDevice, st));
                     unsigned int *flag = ready + ((row0 / BK) >> ready_shift);
@@ -1081,9 +1088,8 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
                 }
             }
             FEO_CUDA(ctx, cudaEventRecord(ctx->ev_join, ss[0]));
-            FEO_CUDA(ctx, cudaEventRecord(ctx->ev_join2, ss[1]));
+            for (int i = 1; i < n_streams; ++i) FEO_CUDA(ctx, cudaEventRecord(ctx->pull_joins[i - 1], ss[i]));
             overlap = true;   // join the side streams behind the matmul kernel
-            two_streams = true;
         } else if (pull) {
             ready = ready_ws;
             ready_need = (unsigned)(BK * feo_ceil_div(N, (size_t)P_PULL_CHUNK));
@@ -1199,7 +1205,7 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
         FEO_LAUNCH_CHECK(ctx);
     }
     if (overlap) FEO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // the workspace is reused by the next call
-    if (two_streams) FEO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));
+    for (int i = 1; i < n_streams; ++i) FEO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pull_joins[i - 1], 0));
     return FEO_OK;
 }
 

@@ -23,6 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--big", action="store_true", help="add the config-3 sized cases (1 GiB per rank)")
+    ap.add_argument("--pull-shapes", type=lambda v: [int(x) for x in v.split(",") if x], default=[], help="extra copy-engine shapes to time: 100 * streams + k-blocks per piece, comma separated")
     ap.add_argument("--only-matmul", action="store_true", help="skip the reductions and the dot: only the config-4 sharded-B matmul (implies --big)")
     args = ap.parse_args()
     import torch
@@ -159,6 +160,10 @@ def main():
             if label == "peer":  # default = auto (copy engines here); the other routes for comparison
                 ctx.tune(L.KNOB_GATHER_OVERLAP, 3)
                 res["peer_copy_engines"] = timed(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
+                for shape in args.pull_shapes:  # copy-engine route, streams x piece size (knob PULL_SHAPE = 100 * streams + k-blocks per piece)
+                    ctx.tune(L.KNOB_PULL_SHAPE, shape)
+                    res[f"peer_copy_engines_{shape // 100}streams_{shape % 100}kb"] = timed(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
+                ctx.tune(L.KNOB_PULL_SHAPE, 0)
                 ctx.tune(L.KNOB_GATHER_OVERLAP, 4)
                 res["peer_in_kernel_pull"] = timed(lambda: sa.matmul(sb, b_sharded=True, algo="tf32x3"))
                 ctx.tune(L.KNOB_GATHER_OVERLAP, 2)
