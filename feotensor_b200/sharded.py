@@ -308,7 +308,7 @@ class CudaEngine:
         return Matrix.from_tensor(A).matmul(Matrix.from_tensor(B), algo=algo)._tensor
 
     def matmul_sharded_b(self, A, b_ptrs, K, N, algo="auto"):
-        """A[M,K] (this rank's rows) times a B whose row panels sit in peer memory: gather fused into the kernel's pre-pass."""
+        """A[M,K] (this rank's rows) times a B whose row panels sit in peer memory: they are pulled while the matmul kernel runs."""
         ctx, M = self.ctx, self.dims(A)[0]
         out = self.empty([M, N], A.dtype)
         arr = (C.c_void_p * len(b_ptrs))(*[C.c_void_p(q) for q in b_ptrs])

@@ -230,9 +230,11 @@ FEO_API int feo_reduce_sharded(feo_comm *comm, int kind, int dtype, void *out, c
  * there) as mapped in THIS process, each bytes_per_part long. */
 FEO_API int feo_comm_gather(feo_comm *comm, void *out, const void *const *parts, size_t bytes_per_part);
 /* DynamicMatrix::matmul (matrix.rs:76-90) with A row-sharded (this rank's [M,K] block, C likewise) and B row-sharded:
- * b_parts[r] = rank r's [K / world, N] panel in peer-mapped memory.  f32 TF32X3: the split / transpose pre-pass pulls
- * the panels over NVLink itself, no gathered copy of B is written; otherwise pull-gather into scratch, then the
- * kernel.  Ends with a barrier, so a panel may be overwritten once the call has completed on its owner's stream. */
+ * b_parts[r] = rank r's [K / world, N] panel in peer-mapped memory.  f32 TF32X3: the panels arrive WHILE the matmul
+ * kernel runs and are consumed k-block by k-block in a rotated order (this rank's own panel first, read in place) --
+ * pulled piecewise by the copy engines, by the matmul kernel itself (TMA bulk copies), or by a gather kernel on a side
+ * stream; otherwise pull-gather into scratch, then the kernel.  Ends with a barrier, so a panel may
+ * be overwritten once the call has completed on its owner's stream. */
 FEO_API int feo_matmul_sharded_b(feo_comm *comm, int algo, int dtype, void *C, const void *A, const void *const *b_parts, size_t M,
                          size_t K, size_t N);
 /* DynamicVector::vecmul (vector.rs:71-78) on identically sharded operands [batch, n_local]. */

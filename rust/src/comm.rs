@@ -111,8 +111,8 @@ impl PeerComm {
     }
 
     /// `DynamicMatrix::matmul` (matrix.rs:76-90) with A row-sharded (`a_local` = this rank's [M, K] rows) and B row-sharded:
-    /// `b_panels[r]` = rank r's [K / world, N] panel, a `PeerWindow` opened here.  The panels are pulled over NVLink by
-    /// the kernel's own pre-pass; returns this rank's [M, N] rows of the product.
+    /// `b_panels[r]` = rank r's [K / world, N] panel, a `PeerWindow` opened here.  The panels are pulled over NVLink while
+    /// the matmul kernel runs; returns this rank's [M, N] rows of the product.
     pub fn matmul_sharded_b<T: DeviceElem>(&self, a_local: &DeviceTensor<T>, b_panels: &[*const c_void], k: usize, n: usize) -> DeviceTensor<T> {
         let m = dims_of(a_local.shape())[0];
         assert_eq!(dims_of(a_local.shape())[1], k, "assertion `left == right` failed (inner dimensions)");
