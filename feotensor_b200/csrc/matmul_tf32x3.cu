@@ -6,11 +6,15 @@
 //   with f32 accumulation in tensor memory.  Error ~ 1e-6 * sum|a||b|: inside the f32 reassociation bound the
 //   reference's own sequential sum obeys, at 3 tensor-core passes instead of the FP32 SIMT pipe.
 //
-// Structure (hand-written PTX; no CUTLASS):
-//   pre-pass   split_rows_kernel     A  -> A_hi, A_lo          [M,K]  (K-major as is)
-//              split_transpose_kernel B -> Bt_hi, Bt_lo        [N,K]  (transposed so both operands are K-major)
-//              ~1.5 GiB of traffic for 8192^3 (0.25 ms) against milliseconds of MMA time.
-//   main       matmul_tf32x3_kernel  one 128 x 256 output tile per CTA, BK = 32 (one 128-byte swizzle atom):
+// Structure (hand-written PTX; no CUTLASS).  Two main kernels share the pre-pass over A and the accumulation scheme:
+//   pre-pass   split_rows_kernel     A  -> A_hi, A_lo          [M,Kp] (K-major as is, zero padded to whole k-blocks)
+//   default    matmul_tf32x3_pair_kernel (further down): tcgen05 cta_group::2, two CTAs per 256 x BN tile, persistent,
+//              B read as raw f32 tiles (MN-major operand) and split hi/lo inside the kernel -- no pre-pass over B;
+//              for a row-sharded B the panels arrive while the kernel runs (copy engines / the kernel's own TMA bulk
+//              copies / a gather kernel, see matmul_tf32x3_run).
+//   fallback   matmul_tf32x3_kernel (round 1; knob MATMUL_TF32_PAIR = 1): one 128 x 256 output tile per CTA, with
+//              split_transpose_kernel B -> Bt_hi, Bt_lo [N,Kp] (transposed so both operands are K-major) in front
+//              (the pair kernel takes this pre-split form too when N % 4 != 0: TMA needs a 16-byte row pitch):
 //              warp 0   TMA producer: cp.async.bulk.tensor (128B swizzle) of A_hi/A_lo/Bt_hi/Bt_lo k-blocks into a
 //                       kStages-deep shared-memory ring, completion on mbarriers (expect_tx)
 //              warp 1   allocates all 512 TMEM columns (two 128x256 f32 accumulators); one lane issues
@@ -20,10 +24,10 @@
 //                       (measured: 83 % of the errors point toward zero and the bias grows linearly with K,
 //                       -1.7e-4 relative at K = 16384 on positive data), so K is cut into chunks of kc k-blocks that
 //                       accumulate into alternating TMEM buffers; these warps drain each finished chunk with
-//                       tcgen05.ld (32x32b.x32) and add it to f32 registers with round-to-nearest, overlapped with
+//                       tcgen05.ld and add it to f32 registers with round-to-nearest, overlapped with
 //                       the MMAs of the next chunk, then write C.
-// Bound: the tensor pipe (3 x 2MNK TF32 flop) -- and, with f32 operands split in two, the L2->SM operand stream
-// (96 KiB per k-block per CTA); see DESIGN.md 4.6 for the measured utilisation.
+// Bound: the tensor pipe (3 x 2MNK TF32 flop; 92.7 % active in the pair kernel at 8192^3, at the clock the power cap
+// allows); see DESIGN.md 4.6 for the measurements.
 #include <cuda.h>
 
 #include "feo_common.cuh"
