@@ -144,11 +144,12 @@ int feo_init(int device, feo_ctx **out) {
         ctx->peer_timeout_ns = sec > 0 ? (unsigned long long)(sec * 1e9) : 0;
     }
     ctx->counters_len = size_t(1) << 20;
-    if (cudaMalloc(&ctx->counters, ctx->counters_len * sizeof(unsigned int)) != cudaSuccess ||
-        cudaMemset(ctx->counters, 0, ctx->counters_len * sizeof(unsigned int)) != cudaSuccess) {
+    if (cudaMalloc(&ctx->counters, (ctx->counters_len + 1) * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(ctx->counters, 0, (ctx->counters_len + 1) * sizeof(unsigned int)) != cudaSuccess) {
         ctx->counters = nullptr;
         ctx->counters_len = 0;  // fall back to the two-launch combine
     }
+    ctx->xtail_ticket = ctx->counters ? ctx->counters + ctx->counters_len : nullptr;
     *out = ctx;
     return FEO_OK;
 }

@@ -60,6 +60,8 @@ struct feo_ctx {
     unsigned long long peer_timeout_ns = 600ull * 1000000000ull;
     unsigned int *counters = nullptr;   // zeroed arrival counters for the fused reduction combine
     size_t counters_len = 0;
+    unsigned int *xtail_ticket = nullptr;  // zeroed CTA counter of the exchange-at-the-tail reductions (the entry behind `counters`)
+    void *xtail_req = nullptr;          // feo_peer::XTailReq of the sharded reduction being issued (peer_sync.cuh), else null
     uint64_t launches = 0;
     size_t l2_persist_bytes = 0;        // persisting-L2 carve-out set by knob BCAST_L2KEEP = 2 (0: none)
     size_t l2_window_max = 0;           // cudaDevAttrMaxAccessPolicyWindowSize

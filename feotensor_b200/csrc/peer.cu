@@ -28,13 +28,11 @@ using namespace feo_peer;
 
 namespace {
 
-enum { X_SUM = 0, X_MEAN = 1, X_VAR = 2, X_MAX = 3, X_MIN = 4 };
-
-template <typename T, int KIND> __device__ __forceinline__ T combine2(T a, T b) {
-    if constexpr (KIND == X_MAX) return feo_max2(a, b);
-    else if constexpr (KIND == X_MIN) return feo_min2(a, b);
-    else return w_add(a, b);
-}
+using feo_red::X_SUM;
+using feo_red::X_MEAN;
+using feo_red::X_VAR;
+using feo_red::X_MAX;
+using feo_red::X_MIN;
 
 // out[o] = epilogue(partial_0[o] (+) partial_1[o] (+) ... ) in rank order; V = elements per access.
 template <typename T, int KIND, int V>
@@ -42,48 +40,8 @@ __global__ void __launch_bounds__(kXThreads) xchg_allreduce_kernel(const __grid_
                                                                    T count, int *arith_flag) {
     asm volatile("griddepcontrol.wait;" ::: "memory");  // the local partial in front of this launch is complete and visible
     signal_and_wait(p);
-    using Vec = AVec<T, V>;
-    const long long nv = p.n / V;
-    for (long long i = (long long)blockIdx.x * kXThreads + threadIdx.x; i < nv; i += (long long)gridDim.x * kXThreads) {
-        Vec part[kMaxPeers], part2[kMaxPeers];
-#pragma unroll
-        for (int r = 0; r < kMaxPeers; ++r) {
-            if (r < p.world) {
-                const Vec *src = reinterpret_cast<const Vec *>(p.win[r] + p.slot_off) + i;
-                part[r] = ld_peer(src);
-                if constexpr (KIND == X_VAR) part2[r] = ld_peer(src + nv);  // M2 follows the n means
-            }
-        }
-        Vec res;
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-            if constexpr (KIND == X_VAR && std::is_floating_point<T>::value) {
-                Acc<T, K_WELFORD> acc;
-                acc.init((T)0);
-#pragma unroll
-                for (int r = 0; r < kMaxPeers; ++r)
-                    if (r < p.world) acc.merge_raw(count, part[r].v[j], part2[r].v[j]);
-                res.v[j] = acc.m2 / divisor;
-            } else if constexpr (KIND == X_VAR) {  // integers: wrapping S1 | S2 partials, exact by the ring identity (K_SUMSQ)
-                T s1 = (T)0, s2 = (T)0;
-#pragma unroll
-                for (int r = 0; r < kMaxPeers; ++r)
-                    if (r < p.world) { s1 = w_add(s1, part[r].v[j]); s2 = w_add(s2, part2[r].v[j]); }
-                const T m = w_div(s1, divisor, arith_flag);
-                T v = w_sub(s2, w_mul(w_mul((T)2, m), s1));
-                v = w_add(v, w_mul(divisor, w_mul(m, m)));
-                res.v[j] = w_div(v, divisor, arith_flag);
-            } else {
-                T a = part[0].v[j];
-#pragma unroll
-                for (int r = 1; r < kMaxPeers; ++r)
-                    if (r < p.world) a = combine2<T, KIND>(a, part[r].v[j]);
-                if constexpr (KIND == X_MEAN) a = w_div(a, divisor, arith_flag);
-                res.v[j] = a;
-            }
-        }
-        reinterpret_cast<Vec *>(out)[i] = res;
-    }
+    feo_red::xchg_combine<T, KIND, V>(p, out, divisor, count, arith_flag, (long long)blockIdx.x * kXThreads + threadIdx.x,
+                                      (long long)gridDim.x * kXThreads);
 }
 
 // Barrier only (n = 0): used before / after kernels that read peers' buffers directly.
@@ -278,11 +236,30 @@ int feo_reduce_sharded(feo_comm *comm, int kind, int dtype, void *out, const voi
     feo_comm_slot(comm, &slot, &slot_bytes);
     if (nout * feo_dtype_size(dtype) * (kind == FEO_VAR ? 2 : 1) > slot_bytes)
         return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "partial exceeds the %zu-byte slot", slot_bytes);
+    if ((kind == FEO_MEAN || kind == FEO_VAR) && !divisor_host) return feo_fail(ctx, FEO_ERR_SHAPE, "mean / var need the divisor");
     // var partials: floats (mean | M2) merged by Chan, integers (S1 | S2) summed and resolved by the ring identity -- one
-    // pass over the data and one exchange either way
-    int rc;
-    if ((rc = feo_reduce_partial(ctx, kind, dtype, slot, in, rank, shape, naxes, axes)) != FEO_OK) return rc;
-    return feo_comm_allreduce(comm, kind, dtype, out, nout, count, divisor_host);
+    // pass over the data and one exchange either way.  The exchange is offered to the local reduction first: if its plan is a
+    // single launch with few outputs, that kernel's last CTA signals, waits and combines itself (one launch, ~3 us less at
+    // config-1 sizes); otherwise the exchange kernel follows with programmatic dependent launch.
+    const XchgParams p = next_exchange(comm, (long long)nout);
+    feo_peer::XTailReq rq{};
+    rq.consumed = false;
+    rq.mean = kind == FEO_MEAN;
+    rq.p = p;
+    rq.out = out;
+    rq.slot = slot;
+    FEO_DISPATCH(ctx, dtype, T, {
+        const T d = divisor_host ? *static_cast<const T *>(divisor_host) : (T)1;
+        const T c = (T)count;
+        memcpy(&rq.divisor_bits, &d, sizeof(T));
+        memcpy(&rq.count_bits, &c, sizeof(T));
+    });
+    ctx->xtail_req = &rq;
+    int rc = feo_reduce_partial(ctx, kind, dtype, slot, in, rank, shape, naxes, axes);
+    ctx->xtail_req = nullptr;
+    if (rc != FEO_OK || rq.consumed) return rc;
+    FEO_DISPATCH(ctx, dtype, T, rc = dispatch_kind<T>(comm, kind, p, out, nout, count, divisor_host));
+    return rc;
 }
 
 // Vector::vecmul (vector.rs:71-78) on two identically sharded vectors: `batch` partial dots into the window, then the sum.

@@ -65,11 +65,12 @@ template <typename V> __device__ __forceinline__ V ld_peer(const V *p) {
     return r;
 }
 
-// Steps 1-2 of the header comment.  Every CTA waits on the local flags; only CTA 0 signals.
-__device__ __forceinline__ void signal_and_wait(const XchgParams &p) {
+// Steps 1-2 of the header comment.  Every CTA waits on the local flags; only one CTA signals (CTA 0 of the exchange
+// kernels; `signals` = true for the one CTA that runs the exchange at the tail of a reduction kernel).
+__device__ __forceinline__ void signal_and_wait(const XchgParams &p, bool signals) {
     if (p.epoch == 0) return;  // nothing to wait for (single rank / local data)
     if (threadIdx.x < p.world) {
-        if (blockIdx.x == 0 && blockIdx.y == 0) {
+        if (signals) {
             __threadfence_system();
             st_release_sys(reinterpret_cast<unsigned long long *>(p.win[threadIdx.x] + p.rank * kFlagStride), p.epoch);
         }
@@ -87,6 +88,21 @@ __device__ __forceinline__ void signal_and_wait(const XchgParams &p) {
     }
     __syncthreads();
 }
+
+__device__ __forceinline__ void signal_and_wait(const XchgParams &p) { signal_and_wait(p, blockIdx.x == 0 && blockIdx.y == 0); }
+
+// A sharded reduction asks the local reduction kernel to run the exchange itself (feo_reduce_sharded -> ctx->xtail_req):
+// when the plan is one launch whose outputs are final (rows kernel, un-split or fused combine) and few, the last CTA to
+// finish signals the peers, waits, pulls and combines -- one launch instead of two.  `consumed` tells the caller whether the
+// planner took the offer; if not it launches the exchange kernel as before.
+struct XTailReq {
+    bool consumed;
+    int mean;                                  // Tensor::mean: divide the sum by `divisor`
+    XchgParams p;
+    void *out;                                 // the replicated result
+    const void *slot;                          // where the final local pass must write its partial (this rank's window slot)
+    unsigned long long divisor_bits, count_bits;  // values of the element type, as bit patterns
+};
 
 // B[K,N] of the sharded matmul as `world` row panels (panel r = rows [r * rows_per_part, ...)), each a peer-mapped pointer.
 struct BParts {

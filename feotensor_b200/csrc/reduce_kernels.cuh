@@ -16,6 +16,7 @@
 #pragma once
 
 #include "feo_common.cuh"
+#include "peer_sync.cuh"
 
 namespace feo_red {
 
@@ -346,6 +347,104 @@ __device__ __noinline__ void warp_combine(T *out, const void *partial, long long
     if (lane == 0) { finalize(m, out, o, nout, fin, divisor, flag); counters[o] = 0; }
 }
 
+// ---- the exchange of a sharded reduction as a device function (csrc/peer.cu's exchange kernel, and the tail of the rows
+// kernel below): element i of the result = epilogue(partial_0[i] (+) partial_1[i] (+) ...) in rank order; V elements per access.
+enum { X_SUM = 0, X_MEAN = 1, X_VAR = 2, X_MAX = 3, X_MIN = 4 };
+template <typename T, int XK, int V>
+__device__ __forceinline__ void xchg_combine(const feo_peer::XchgParams &p, T *__restrict__ out, T divisor, T count, int *arith_flag,
+                                             long long first, long long stride) {
+    using feo_peer::kMaxPeers;
+    using feo_peer::ld_peer;
+    using Vec = AVec<T, V>;
+    const long long nv = p.n / V;
+    for (long long i = first; i < nv; i += stride) {
+        Vec part[kMaxPeers], part2[kMaxPeers];
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) {
+            if (r < p.world) {
+                const Vec *src = reinterpret_cast<const Vec *>(p.win[r] + p.slot_off) + i;
+                part[r] = ld_peer(src);
+                if constexpr (XK == X_VAR) part2[r] = ld_peer(src + nv);  // M2 follows the n means
+            }
+        }
+        Vec res;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            if constexpr (XK == X_VAR && std::is_floating_point<T>::value) {
+                Acc<T, K_WELFORD> acc;
+                acc.init((T)0);
+#pragma unroll
+                for (int r = 0; r < kMaxPeers; ++r)
+                    if (r < p.world) acc.merge_raw(count, part[r].v[j], part2[r].v[j]);
+                res.v[j] = acc.m2 / divisor;
+            } else if constexpr (XK == X_VAR) {  // integers: wrapping S1 | S2 partials, exact by the ring identity (K_SUMSQ)
+                T s1 = (T)0, s2 = (T)0;
+#pragma unroll
+                for (int r = 0; r < kMaxPeers; ++r)
+                    if (r < p.world) { s1 = w_add(s1, part[r].v[j]); s2 = w_add(s2, part2[r].v[j]); }
+                const T m = w_div(s1, divisor, arith_flag);
+                T v = w_sub(s2, w_mul(w_mul((T)2, m), s1));
+                v = w_add(v, w_mul(divisor, w_mul(m, m)));
+                res.v[j] = w_div(v, divisor, arith_flag);
+            } else {
+                T a = part[0].v[j];
+#pragma unroll
+                for (int r = 1; r < kMaxPeers; ++r)
+                    if (r < p.world) {
+                        if constexpr (XK == X_MAX) a = feo_max2(a, part[r].v[j]);
+                        else if constexpr (XK == X_MIN) a = feo_min2(a, part[r].v[j]);
+                        else a = w_add(a, part[r].v[j]);
+                    }
+                if constexpr (XK == X_MEAN) a = w_div(a, divisor, arith_flag);
+                res.v[j] = a;
+            }
+        }
+        reinterpret_cast<Vec *>(out)[i] = res;
+    }
+}
+
+// Exchange at the tail of a reduction kernel (see feo_peer::XTailReq): plain data, so that Geom stays a kernel parameter.
+struct XTail {
+    int on, mean;
+    feo_peer::XchgParams p;
+    void *out;
+    unsigned long long divisor_bits, count_bits;
+    unsigned int *ticket;
+};
+template <typename T> __device__ __forceinline__ T xtail_value(unsigned long long bits) {
+    T v;
+    __builtin_memcpy(&v, &bits, sizeof(T));
+    return v;
+}
+// Called by EVERY thread of EVERY CTA at the end of the kernel, after this CTA's outputs have been written: the CTA that
+// takes the last ticket sees all of them (fence + atomic, the usual last-block pattern) and runs the whole exchange.
+template <typename T, int KIND>
+__device__ __forceinline__ void run_xtail(const XTail &xt, int *arith_flag) {
+    if constexpr (KIND == K_SUM || KIND == K_MAX || KIND == K_MIN || KIND == K_WELFORD || KIND == K_SUMSQ) {
+        __shared__ unsigned int s_ticket;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket = atomicAdd(xt.ticket, 1u);
+        __syncthreads();
+        if (s_ticket != gridDim.x - 1) return;
+        if (threadIdx.x == 0) *xt.ticket = 0;  // ready for the next launch on this stream
+        __threadfence();
+        feo_peer::signal_and_wait(xt.p, true);
+        T *out = static_cast<T *>(xt.out);
+        const T divisor = xtail_value<T>(xt.divisor_bits), count = xtail_value<T>(xt.count_bits);
+        if constexpr (KIND == K_SUM) {
+            if (xt.mean) xchg_combine<T, X_MEAN, 1>(xt.p, out, divisor, count, arith_flag, threadIdx.x, blockDim.x);
+            else xchg_combine<T, X_SUM, 1>(xt.p, out, divisor, count, arith_flag, threadIdx.x, blockDim.x);
+        } else if constexpr (KIND == K_MAX) {
+            xchg_combine<T, X_MAX, 1>(xt.p, out, divisor, count, arith_flag, threadIdx.x, blockDim.x);
+        } else if constexpr (KIND == K_MIN) {
+            xchg_combine<T, X_MIN, 1>(xt.p, out, divisor, count, arith_flag, threadIdx.x, blockDim.x);
+        } else {
+            xchg_combine<T, X_VAR, 1>(xt.p, out, divisor, count, arith_flag, threadIdx.x, blockDim.x);
+        }
+    }
+}
+
 struct Geom {
     long long K1, R1, K2, R2;  // canonical extents
     long long S, S1, S2;       // splits: S = S1 (over r1) * S2 (over r2 vectors)
@@ -356,6 +455,7 @@ struct Geom {
     int lanes;                 // rows kernel: 32 (warp per output) or 256 (block per output)
     int lx;                    // rows kernel: lanes along the row (power of two <= lanes); lanes / lx rows at a time
     unsigned int *counters;    // per-output arrival counters for the fused combine (nullptr: two-stage)
+    XTail xt;                  // xt.on: the last CTA of the (rows) kernel runs the exchange of the sharded reduction
 };
 
 // ---- cols: in[k1][r1][k2] -> out[k1][k2], threads along k2 ---------------------------------------------
@@ -894,33 +994,38 @@ __global__ void __launch_bounds__(kThreads, 4) reduce_rows_kernel(T *__restrict_
                 warp_combine<T, KIND>(out, partial, o, G.nout, G.S, G.fin, divisor, flag, G.counters, lane);
             }
         }
-        return;
-    }
-    // block per (output, split): merge the eight warp results in warp order
-    __shared__ unsigned int s_last;
-    const int warp = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) smem[warp] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int last = 0;
-        if (active) {
-            Acc<T, KIND> t = smem[0];
+    } else {
+        // block per (output, split): merge the eight warp results in warp order
+        __shared__ unsigned int s_last;
+        const int warp = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) smem[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int last = 0;
+            if (active) {
+                Acc<T, KIND> t = smem[0];
 #pragma unroll
-            for (int w = 1; w < kThreads / 32; ++w) t.merge(smem[w]);
-            emit(t, out, partial, o, s, G.nout, G.S, G.fin, divisor, flag, (unsigned int *)nullptr);
-            if (fused) {
+                for (int w = 1; w < kThreads / 32; ++w) t.merge(smem[w]);
+                emit(t, out, partial, o, s, G.nout, G.S, G.fin, divisor, flag, (unsigned int *)nullptr);
+                if (fused) {
+                    __threadfence();
+                    last = (atomicAdd(&G.counters[o], 1u) == (unsigned int)(G.S - 1));
+                }
+            }
+            s_last = last;
+        }
+        if (fused) {
+            __syncthreads();
+            if (s_last && warp == 0) {
                 __threadfence();
-                last = (atomicAdd(&G.counters[o], 1u) == (unsigned int)(G.S - 1));
+                warp_combine<T, KIND>(out, partial, o, G.nout, G.S, G.fin, divisor, flag, G.counters, threadIdx.x & 31);
             }
         }
-        s_last = last;
     }
-    if (fused) {
-        __syncthreads();
-        if (s_last && warp == 0) {
-            __threadfence();
-            warp_combine<T, KIND>(out, partial, o, G.nout, G.S, G.fin, divisor, flag, G.counters, threadIdx.x & 31);
-        }
+    // sharded reduction with the exchange at the tail: every output of this launch is final now (un-split, or merged by the
+    // last arriver above); the last CTA to get here signals the peers, waits, pulls and combines
+    if constexpr (LOADER == LD_PLAIN) {
+        if (G.xt.on) run_xtail<T, KIND>(G.xt, flag);
     }
 }
 
@@ -1292,6 +1397,23 @@ int run_canonical(feo_ctx *ctx, const Canon &c, T *out, const T *in, const T *in
         const long long units = G.nout * G.S;
         const long long blocks = feo_ceil_div((size_t)units, (size_t)(kThreads / G.lanes));
         if (blocks > 0x7fffffffLL) return feo_fail(ctx, FEO_ERR_UNSUPPORTED, "reduction grid too large");
+        if constexpr (LOADER == LD_PLAIN && (KIND == K_SUM || KIND == K_MAX || KIND == K_MIN || KIND == K_WELFORD || KIND == K_SUMSQ)) {
+            // a sharded reduction whose local part is this one launch with few, final outputs: the kernel's last CTA runs
+            // the exchange itself (feo_reduce_sharded then skips the exchange kernel)
+            auto *rq = static_cast<feo_peer::XTailReq *>(ctx->xtail_req);
+            const bool final_in_one = (G.S == 1) || (G.counters != nullptr);
+            if (rq && !rq->consumed && (const void *)out == rq->slot && final_in_one && G.nout <= 8192 && ctx->xtail_ticket &&
+                ctx->knobs[FEO_KNOB_REDUCE_FUSE] != 1) {
+                G.xt.on = 1;
+                G.xt.mean = rq->mean;
+                G.xt.p = rq->p;
+                G.xt.out = rq->out;
+                G.xt.divisor_bits = rq->divisor_bits;
+                G.xt.count_bits = rq->count_bits;
+                G.xt.ticket = ctx->xtail_ticket;
+                rq->consumed = true;
+            }
+        }
         constexpr int L = (LOADER == LD_MUL || LOADER == LD_MATVEC) ? LOADER : LD_PLAIN;
         if (vec) reduce_rows_kernel<T, KIND, L, true><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
         else reduce_rows_kernel<T, KIND, L, false><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(out, partial, in, in2, aux, G, divisor, flag);
