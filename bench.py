@@ -1062,6 +1062,7 @@ def main():
                 "d2h_bytes_per_step": 4 * ROWS_PER_RANK * D * D, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                 "host_numa_node": numa_node, "ring_slots": RING, "ring_alloc": "feo_host_alloc",
                 "d2h_ceiling_gbs": d2h_ceiling, "frac_of_d2h_ceiling": (world * 4.0 * ROWS_PER_RANK * D * D * e2e_steps / (e2e_ms * 1e-3) / 1e9) / d2h_ceiling,
+                "ceiling_gbs": d2h_ceiling, "frac_of_ceiling": (world * 4.0 * ROWS_PER_RANK * D * D * e2e_steps / (e2e_ms * 1e-3) / 1e9) / d2h_ceiling,
                 "ceiling_how": f"{world} rank(s) at once, plain cudaMemcpyAsync of the same 32 x 1 GiB slabs into the same pinned ring, max over ranks"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
