@@ -70,7 +70,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "25", "-f", self.path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                                          "-lms", "50", "-f", self.path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
