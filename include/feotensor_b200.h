@@ -223,7 +223,9 @@ FEO_API int feo_comm_allreduce(feo_comm *comm, int kind, int dtype, void *out, s
 /* Tensor::{sum,mean,var,max,min} (tensor.rs:70-307) of a tensor sharded on its leading axis with
  * axis 0 among the removed axes: `shape` is the LOCAL block, *divisor_host the counted-in-T divisor
  * of the GLOBAL shape (feo_reduce_divisor).  Local one-pass reduction written straight into the
- * window, then the exchange kernel (var: one pass and one exchange for floats and integers alike). */
+ * window, then the exchange -- by the reduction kernel's own last CTA when the local plan is a single
+ * launch with few outputs, else by the exchange kernel (var: one pass and one exchange for floats and
+ * integers alike). */
 FEO_API int feo_reduce_sharded(feo_comm *comm, int kind, int dtype, void *out, const void *in, int rank, const size_t *shape,
                        int naxes, const size_t *axes, const void *divisor_host);
 /* All-gather by pulling over NVLink: out = part 0 | part 1 | ...; parts[r] is rank r's buffer (feo_peer_alloc'ed
