@@ -986,7 +986,15 @@ def main():
     a_host, b_host = host_buffer(a.numel() * 4), host_buffer(b.numel() * 4)
     C.memmove(a_host, a_h.ctypes.data, a.numel() * 4)
     C.memmove(b_host, b_h.ctypes.data, b.numel() * 4)
-    ring = [host_buffer(4 * slab_elems) for _ in range(RING)]
+    ring = []
+    for _ in range(RING):
+        try:
+            ring.append(host_buffer(4 * slab_elems))
+        except feo.BackendError:
+            if len(ring) < 2:  # two slots are the minimum for copy / compute overlap; fewer means the host cannot pin enough memory
+                raise
+            break
+    RING = len(ring)
     copy_stream = torch.cuda.Stream()
     main_stream = torch.cuda.current_stream()
     ctx_copy = feo.Context(local)  # second context on the copy stream: the D2H leg goes through the C ABI too
