@@ -530,4 +530,70 @@ private:
     int rank_, world_;
 };
 
+// ---- the NCCL route of the same exchanges, issued inside the C ABI (csrc/nccl_route.cu) ------------------------------------
+// One process (or thread) per GPU: rank 0 creates the id, the host program's own rendezvous (MPI_Bcast, a file, a socket)
+// carries its 128 bytes to the other ranks, every rank constructs an NcclComm.  libnccl.so.2 is dlopen'ed by the library.
+using NcclId = std::array<unsigned char, FEO_NCCL_UNIQUE_ID_BYTES>;
+
+class NcclComm {
+public:
+    static NcclId unique_id() {
+        NcclId id{};
+        if (feo_nccl_unique_id(id.data()) != FEO_OK) throw BackendError("feo_nccl_unique_id failed: is libnccl.so.2 on the loader path (FEO_NCCL_LIB)?");
+        return id;
+    }
+    NcclComm(std::shared_ptr<Context> ctx, const NcclId &id, int rank, int world) : ctx_(std::move(ctx)), rank_(rank), world_(world) {
+        ctx_->check(feo_nccl_comm_create(ctx_->raw(), id.data(), rank, world, &raw_));
+    }
+    ~NcclComm() {
+        feo_sync(ctx_->raw());
+        feo_nccl_comm_destroy(raw_);
+    }
+    NcclComm(const NcclComm &) = delete;
+    NcclComm &operator=(const NcclComm &) = delete;
+    int rank() const { return rank_; }
+    int world() const { return world_; }
+
+    // Tensor::{sum,mean,var,max,min} (tensor.rs:70-307) of the GLOBAL tensor whose block of leading rows is `local`: local
+    // one-pass partial, ncclAllReduce (var: ncclAllGather + rank-ordered merge), epilogue.  Same contract as PeerComm::reduce.
+    template <class T> Tensor<T> reduce(int kind, const Tensor<T> &local, const Shape &global, const Axes &axes) const {
+        int out_rank = 0;
+        std::vector<size_t> od(global.order() ? global.order() : 1);
+        if (feo_reduce_shape((int)global.order(), global.dims().data(), (int)axes.size(), axes.data(), &out_rank, od.data()) != FEO_OK)
+            throw Panic("axes must be strictly ascending, unique and < order (the reference panics)");
+        od.resize((size_t)out_rank);
+        T divisor{};
+        feo_reduce_divisor(Tensor<T>::DT, (int)global.order(), global.dims().data(), (int)axes.size(), axes.data(), &divisor);
+        Axes local_axes = axes;
+        if (local_axes.empty())
+            for (size_t d = 0; d < local.shape().order(); ++d) local_axes.push_back(d);
+        Shape os(od);
+        Tensor<T> out(os, DeviceStorage<T>(local.data().ctx(), os.size()));
+        ctx_->check(feo_reduce_sharded_nccl(raw_, kind, Tensor<T>::DT, out.ptr(), local.ptr(), (int)local.shape().order(),
+                                            local.shape().dims().data(), (int)local_axes.size(), local_axes.data(), &divisor));
+        return out;
+    }
+    // DynamicVector::vecmul (vector.rs:71-78) on two identically sharded vectors: partial dots, then ncclAllReduce.
+    template <class T> Tensor<T> dot(const Tensor<T> &a, const Tensor<T> &b) const {
+        if (a.shape() != b.shape()) throw Panic("assertion failed: self.shape() == rhs.shape()");
+        Tensor<T> out(Shape({1}), DeviceStorage<T>(a.data().ctx(), 1));
+        ctx_->check(feo_dot_sharded_nccl(raw_, Tensor<T>::DT, out.ptr(), a.ptr(), b.ptr(), 1, a.size()));
+        return out;
+    }
+    // DynamicMatrix::matmul (matrix.rs:76-90), A and B row-sharded: ncclAllGather of B (b_local = this rank's [K / world, N]
+    // panel), then the local kernel; returns this rank's [M, N] rows.
+    template <class T> Tensor<T> matmul_sharded_b(const Tensor<T> &a_local, const Tensor<T> &b_local, size_t K, size_t N) const {
+        const size_t M = a_local.shape()[0];
+        if (a_local.shape()[1] != K) throw Panic("assertion `left == right` failed");
+        Tensor<T> out(Shape({M, N}), DeviceStorage<T>(a_local.data().ctx(), M * N));
+        ctx_->check(feo_matmul_sharded_b_nccl(raw_, FEO_MATMUL_AUTO, Tensor<T>::DT, out.ptr(), a_local.ptr(), b_local.ptr(), M, K, N));
+        return out;
+    }
+
+private:
+    std::shared_ptr<Context> ctx_;
+    feo_nccl *raw_ = nullptr;
+    int rank_, world_;
+};
+
 }  // namespace feo

@@ -62,6 +62,37 @@ int main(int argc, char **) {
     assert os.access(exe, os.X_OK)
 
 
+def test_cpp_nccl_communicator_api_compiles(tmp_path):
+    """The NCCL route of the C++ host API (feo::NcclComm over feo_nccl_*: NCCL issued inside the C ABI, no Python, no
+    torch.distributed) instantiates against the C ABI for every dtype."""
+    src = tmp_path / "nccl_api.cpp"
+    src.write_text("""
+#include "feotensor.hpp"
+template <class T> void use(feo::NcclComm &c, const feo::Tensor<T> &x, const feo::Shape &g) {
+    (void)c.reduce(FEO_VAR, x, g, feo::Axes{0});
+    (void)c.reduce(FEO_MAX, x, g, feo::Axes{});
+    (void)c.dot(x, x);
+    (void)c.matmul_sharded_b(x, x, 4, 4);
+}
+int main(int argc, char **) {
+    if (argc > 1000) {  // never runs: this program only has to compile and link
+        auto ctx = std::make_shared<feo::Context>(0);
+        const feo::NcclId id = feo::NcclComm::unique_id();   // rank 0; the host's own rendezvous carries it to the others
+        feo::NcclComm comm(ctx, id, 0, 1);
+        feo::Shape g({4, 4});
+        use(comm, feo::Tensor<float>::zeros(g), g); use(comm, feo::Tensor<double>::zeros(g), g);
+        use(comm, feo::Tensor<int32_t>::zeros(g), g); use(comm, feo::Tensor<int64_t>::zeros(g), g); use(comm, feo::Tensor<uint32_t>::zeros(g), g);
+        return comm.rank() + comm.world();
+    }
+    return 0;
+}
+""")
+    exe = tmp_path / "nccl_api"
+    subprocess.run(["g++", "-std=c++17", "-O0", "-Wall", "-I" + os.path.join(ROOT, "include"), str(src), "-L" + LIBDIR, "-lfeotensor_b200",
+                    "-Wl,-rpath," + LIBDIR, "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
 @pytest.mark.gpu
 def test_cpp_port_of_reference_tests_passes_on_gpu():
     exe = _build()
