@@ -1029,17 +1029,14 @@ int matmul_tf32x3_run(feo_ctx *ctx, void *C, const void *A, const void *B, const
     unsigned int *ready = nullptr;
     unsigned int ready_need = 0;
     int kb_rot = 0;
-    bool overlap = false, pull = false, own_direct = false;
+    bool overlap = false, pull = false, own_direct = false;  // own_direct: this rank's panel is read in place (mb_lo), not copied
     int n_streams = 1;    // copy-engine route: side streams in use (their join events are waited for behind the matmul kernel)
-    int ready_shift = 0;  // one readiness counter per 2^ready_shift k-blocks (copy-engine route: one per piece)  // own_direct: this rank's panel is read in place (mb_lo), not copied
+    int ready_shift = 0;  // one readiness counter per 2^ready_shift k-blocks (copy-engine route: one per piece)
     if (parts) {
         kb_rot = (int)(((size_t)sync->rank * parts->rows_per_part) / BK);
         const int kn = ctx->knobs[FEO_KNOB_GATHER_OVERLAP];
         pull = raw_b && (kn == 4 || (kn == 0 && parts->rows_per_part % BK != 0));
-        // 3: the copy engines pull.  Each remote panel is cut into pieces of kPieceKb k-blocks; a piece is one peer
-        // cudaMemcpyAsync into the local raw B followed by a tiny host-to-device copy of ones onto its readiness counters -- both
-        // run on copy engines, so they make progress while the persistent matmul kernel owns every SM.  Needs whole k-blocks
-        // per panel (the own panel is then read in place through mb_lo and never copied).
+        // copy engines: needs whole k-blocks per panel (the own panel is then read in place through mb_lo and never copied)
         const bool ce = raw_b && (kn == 3 || kn == 0) && parts->rows_per_part % BK == 0 && feo_side_stream(ctx) == FEO_OK;
         if (ce) {
             // Pieces of up to 16 k-blocks (16 MiB at N = 8192; a power of two that divides the panel), dealt alternately to two side
